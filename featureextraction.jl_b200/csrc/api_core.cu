@@ -1,0 +1,178 @@
+// api_core.cu -- contexts, error text, device arena, event timers.
+#include <stdarg.h>
+#include "fx_kernels.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void fx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* fx_last_error(void) { return g_err; }
+extern "C" int fx_version(void) { return 100; }
+
+int fx_arena_reserve(fx_ctx* ctx, size_t bytes) {
+    bytes = fx_align256(bytes) + 4096;
+    if (bytes <= ctx->arena_cap) return 0;
+    if (ctx->arena) {
+        FX_CUDA(cudaStreamSynchronize(ctx->stream));
+        FX_CUDA(cudaFree(ctx->arena));
+        ctx->arena = nullptr;
+        ctx->arena_cap = 0;
+    }
+    cudaError_t e = cudaMalloc((void**)&ctx->arena, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fx_set_error("out of device memory: workspace of %.2f GB refused (%s)", bytes / 1e9,
+                     cudaGetErrorString(e));
+        return FX_ERR_OOM;
+    }
+    ctx->arena_cap = bytes;
+    ctx->arena_off = 0;
+    return 0;
+}
+
+void* fx_arena_alloc(fx_ctx* ctx, size_t bytes) {
+    bytes = fx_align256(bytes);
+    if (ctx->arena_off + bytes > ctx->arena_cap) return nullptr;   // callers reserve first
+    void* p = ctx->arena + ctx->arena_off;
+    ctx->arena_off += bytes;
+    return p;
+}
+
+cudaEvent_t FxTimer::get_event() {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+void FxTimer::begin(double* acc) {
+    Span sp;
+    sp.a = get_event();
+    sp.b = get_event();
+    sp.acc = acc;
+    cudaEventRecord(sp.a, ctx->stream);
+    spans.push_back(sp);
+}
+void FxTimer::end() { cudaEventRecord(spans.back().b, ctx->stream); }
+int FxTimer::resolve() {
+    for (auto& sp : spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.acc += ms;
+        else cudaGetLastError();
+    }
+    spans.clear();
+    ctx->ev_used = 0;
+    return 0;
+}
+
+static int ctx_common_init(int device, fx_ctx** out) {
+    if (!out) { fx_set_error("fx_init: out is NULL"); return -2; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fx_set_error("fx_init: no CUDA device available (%s); this library has no CPU fallback",
+                     cudaGetErrorString(e));
+        return FX_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { fx_set_error("fx_init: device %d out of range", device); return -1; }
+    FX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        fx_set_error("fx_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                     device, prop.major, prop.minor);
+        return FX_ERR_CUDA;
+    }
+    fx_ctx* c = new fx_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    FX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    c->pinned_cap = 4096;
+    FX_CUDA(cudaMallocHost((void**)&c->pinned, c->pinned_cap * sizeof(double)));
+    *out = c;
+    return 0;
+}
+
+extern "C" int fx_init(int device, fx_ctx** out) { return ctx_common_init(device, out); }
+
+extern "C" int fx_comm_unique_id(void* id128) {
+    if (!id128) return -1;
+    return fxcomm_unique_id(id128);
+}
+
+extern "C" int fx_init_distributed(int device, int rank, int world, const void* id128, fx_ctx** out) {
+    if (world < 1 || rank < 0 || rank >= world) { fx_set_error("bad rank/world %d/%d", rank, world); return -2; }
+    if (!id128 && world > 1) return -4;
+    FX_TRY(ctx_common_init(device, out));
+    fx_ctx* c = *out;
+    c->rank = rank;
+    c->world = world;
+    if (world > 1) {
+        int r = fxcomm_create(rank, world, id128, &c->comm);
+        if (r) { fx_shutdown(c); *out = nullptr; return r; }
+    }
+    return 0;
+}
+
+extern "C" int fx_set_stream(fx_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        FX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return 0;
+}
+
+extern "C" int fx_ctx_info(const fx_ctx* ctx, int* device, int* rank, int* world, int* sm_count) {
+    if (!ctx) return -1;
+    if (device) *device = ctx->device;
+    if (rank) *rank = ctx->rank;
+    if (world) *world = ctx->world;
+    if (sm_count) *sm_count = ctx->sm_count;
+    return 0;
+}
+
+extern "C" void fx_shutdown(fx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) fxcomm_destroy(ctx->comm);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void fx_model_free(fx_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->Xp);
+    cudaFree(m->norms);
+    cudaFree(m->W);
+    cudaFree(m->bias);
+    cudaFree(m->colmean);
+    delete m;
+}
+
+extern "C" int fx_model_info(const fx_model* m, int64_t* n, int64_t* d, int* k, int* kernel_id) {
+    if (!m) return -1;
+    if (n) *n = m->n;
+    if (d) *d = m->d;
+    if (k) *k = m->k;
+    if (kernel_id) *kernel_id = m->kernel_id;
+    return 0;
+}

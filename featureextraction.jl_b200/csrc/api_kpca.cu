@@ -1,0 +1,457 @@
+// api_kpca.cu -- C ABI: KPCA fit (kpca, /root/reference/src/kpca.jl:49-57) and the exposed
+// building blocks (Gram, centring, K*V, small eigensolver).
+#include "fx_kernels.cuh"
+#include <math.h>
+
+namespace {
+
+struct TotalTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int start(fx_ctx* ctx) {
+        FX_CUDA(cudaEventCreate(&a));
+        FX_CUDA(cudaEventCreate(&b));
+        FX_CUDA(cudaEventRecord(a, ctx->stream));
+        return 0;
+    }
+    int stop(fx_ctx* ctx, double* ms) {
+        FX_CUDA(cudaEventRecord(b, ctx->stream));
+        FX_CUDA(cudaEventSynchronize(b));
+        float f = 0.f;
+        FX_CUDA(cudaEventElapsedTime(&f, a, b));
+        *ms = f;
+        return 0;
+    }
+    ~TotalTimer() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+struct ModelGuard {
+    fx_model* m = nullptr;
+    ~ModelGuard() { if (m) fx_model_free(m); }
+    fx_model* release() { fx_model* r = m; m = nullptr; return r; }
+};
+
+int dmalloc(double** p, size_t doubles) {
+    cudaError_t e = cudaMalloc((void**)p, doubles * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fx_set_error("out of device memory allocating %.3f GB for the model", doubles * 8 / 1e9);
+        return FX_ERR_OOM;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// Shared by KPCA and KLDA fits: pads X into feature-major device storage and builds this rank's
+// row block of K (optionally centred).  All buffers come from the arena (already reserved).
+struct GramStage {
+    int64_t n, d, ld, n_ld, d_pad, row0, rows_valid;
+    double *Xp, *norms, *K, *rowpart, *rowsum, *colmean, *scal;   // scal[0]=grand mean, scal[1]=trace
+};
+
+size_t fx_gramstage_bytes(int64_t ld, int64_t n_ld, int64_t d_pad, bool center) {
+    size_t t = 0;
+    t += fx_align256((size_t)d_pad * n_ld * 8);
+    t += fx_align256((size_t)n_ld * 8) * 4;
+    t += fx_align256((size_t)ld * n_ld * 8);
+    if (center) t += fx_align256((size_t)(n_ld / 64) * ld * 8);
+    t += 4096;
+    return t;
+}
+
+int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int64_t ldx,
+                     int kernel_id, const double* kp, bool center, int variant, FxTimer& tm,
+                     fx_stats* st) {
+    cudaStream_t s = ctx->stream;
+    g.Xp = (double*)fx_arena_alloc(ctx, (size_t)g.d_pad * g.n_ld * 8);
+    g.norms = (double*)fx_arena_alloc(ctx, (size_t)g.n_ld * 8);
+    g.rowsum = (double*)fx_arena_alloc(ctx, (size_t)g.n_ld * 8);
+    g.colmean = (double*)fx_arena_alloc(ctx, (size_t)g.n_ld * 8);
+    g.scal = (double*)fx_arena_alloc(ctx, 256);
+    g.K = (double*)fx_arena_alloc(ctx, (size_t)g.ld * g.n_ld * 8);
+    g.rowpart = center ? (double*)fx_arena_alloc(ctx, (size_t)(g.n_ld / 64) * g.ld * 8) : nullptr;
+    if (!g.Xp || !g.norms || !g.rowsum || !g.colmean || !g.scal || !g.K || (center && !g.rowpart)) {
+        fx_set_error("internal: arena too small for the Gram stage");
+        return FX_ERR_OOM;
+    }
+    tm.begin(&st->h2d_ms);
+    FX_CUDA(cudaMemsetAsync(g.Xp, 0, (size_t)g.d_pad * g.n_ld * 8, s));
+    FX_CUDA(cudaMemcpy2DAsync(g.Xp, g.n_ld * 8, X, ldx * 8, g.n * 8, g.d,
+                              x_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    tm.end();
+    if (!x_dev) st->h2d_bytes += g.n * g.d * 8;
+    FX_CUDA(cudaMemsetAsync(g.colmean, 0, (size_t)g.n_ld * 8, s));
+    FX_CUDA(cudaMemsetAsync(g.scal, 0, 256, s));
+    FX_TRY(fx_launch_rownorms(ctx, g.Xp, g.n_ld, g.n_ld, g.d_pad, g.norms));
+
+    GramArgs ga;
+    ga.A = g.Xp + g.row0; ga.lda = g.n_ld; ga.B = g.Xp; ga.ldb = g.n_ld;
+    ga.na = g.norms + g.row0; ga.nb = g.norms; ga.d_pad = g.d_pad;
+    ga.K = g.K; ga.ldk = g.n_ld; ga.rows_pad = g.ld; ga.rows_valid = g.rows_valid;
+    ga.cols_valid = g.n; ga.diag_shift = g.row0; ga.rowpart = g.rowpart;
+    ga.kernel_id = kernel_id; ga.kp[0] = kp[0]; ga.kp[1] = kp[1]; ga.kp[2] = kp[2];
+    tm.begin(&st->gram_ms);
+    FX_TRY(fx_launch_gram(ctx, ga, variant));
+    tm.end();
+    st->gram_launches++;
+
+    if (center) {
+        // column sums == row sums (K symmetric): local rows, then all-gather
+        double* rs_loc = g.rowsum + g.row0;
+        tm.begin(&st->center_ms);
+        FX_TRY(fx_launch_rowpart_reduce(ctx, g.rowpart, g.n_ld / 64, g.ld, rs_loc));
+        tm.end();
+        if (ctx->world > 1) {
+            tm.begin(&st->comm_ms);
+            FX_TRY(fxcomm_allgather(ctx->comm, rs_loc, g.rowsum, (size_t)g.ld, s));
+            tm.end();
+        }
+        tm.begin(&st->center_ms);
+        FX_TRY(fx_launch_means(ctx, g.rowsum, g.n, g.n_ld, g.colmean, g.scal));
+        FX_TRY(fx_launch_center(ctx, g.K, g.n_ld, g.rows_valid, g.n, g.row0, g.colmean, g.scal));
+        tm.end();
+        st->center_launches++;
+    }
+    FX_TRY(fx_launch_trace(ctx, g.K, g.n_ld, g.rows_valid, g.row0, g.scal + 1));
+    if (ctx->world > 1) {
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allreduce_sum(ctx->comm, g.scal + 1, 1, s));
+        tm.end();
+    }
+    return 0;
+}
+
+// Builds the persistent model (own allocations) from arena-resident pieces.
+int fx_model_build(fx_ctx* ctx, const GramStage& g, int kernel_id, const double* kp, int k,
+                   const double* W /* [kpad][n_ld] device */, bool centered, bool is_klda,
+                   fx_model** out) {
+    cudaStream_t s = ctx->stream;
+    ModelGuard mg;
+    mg.m = new fx_model();
+    fx_model* m = mg.m;
+    m->device = ctx->device; m->n = g.n; m->d = g.d; m->n_ld = g.n_ld; m->d_pad = g.d_pad;
+    m->k = k; m->k_pad = (int)round_up(k, 8); m->kernel_id = kernel_id;
+    m->kp[0] = kp[0]; m->kp[1] = kp[1]; m->kp[2] = kp[2];
+    m->centered = centered ? 1 : 0; m->is_klda = is_klda ? 1 : 0;
+    FX_TRY(dmalloc(&m->Xp, (size_t)g.d_pad * g.n_ld));
+    FX_TRY(dmalloc(&m->norms, g.n_ld));
+    FX_TRY(dmalloc(&m->W, (size_t)m->k_pad * g.n_ld));
+    FX_TRY(dmalloc(&m->bias, 64));
+    FX_TRY(dmalloc(&m->colmean, g.n_ld));
+    FX_CUDA(cudaMemcpyAsync(m->Xp, g.Xp, (size_t)g.d_pad * g.n_ld * 8, cudaMemcpyDeviceToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(m->norms, g.norms, (size_t)g.n_ld * 8, cudaMemcpyDeviceToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(m->W, W, (size_t)m->k_pad * g.n_ld * 8, cudaMemcpyDeviceToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(m->colmean, g.colmean, (size_t)g.n_ld * 8, cudaMemcpyDeviceToDevice, s));
+    FX_CUDA(cudaMemsetAsync(m->bias, 0, 64 * 8, s));
+    if (centered) FX_TRY(fx_launch_bias(ctx, m->colmean, m->W, g.n_ld, g.n, m->k_pad, m->bias));
+    *out = mg.release();
+    return 0;
+}
+
+static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, int64_t d, int64_t ldx,
+                         int kernel_id, const double* kparams, int k, int center, double alpha,
+                         double eps, const fx_solver_opts* opts, double* V, int64_t ldv,
+                         double* lambda, fx_model** model, fx_stats* stats) {
+    fx_stats local;
+    fx_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (model) *model = nullptr;
+    if (!ctx) { fx_set_error("kpca_fit: ctx is NULL"); return -1; }
+    if (!X) { fx_set_error("kpca_fit: X is NULL"); return -2; }
+    if (n < 2) { fx_set_error("kpca_fit: need n >= 2 observations (got %lld)", (long long)n); return -3; }
+    if (d < 1) { fx_set_error("kpca_fit: need d >= 1"); return -4; }
+    if (ldx < n) { fx_set_error("kpca_fit: ldx < n (DimensionMismatch)"); return -5; }
+    double kpv[3]; int ipow;
+    if (!kparams || fx_make_kernel_map(kernel_id, kparams, &ipow, kpv)) {
+        fx_set_error("kpca_fit: unknown kernel id %d or invalid kernel parameters", kernel_id);
+        return kparams ? -6 : -7;
+    }
+    if (k < 1 || k > n) { fx_set_error("kpca_fit: k=%d outside 1..n", k); return -8; }
+    if (!(alpha >= 0.0 && alpha <= 1.0)) { fx_set_error("kpca_fit: alpha must lie in [0,1]"); return -10; }
+    if (!(eps >= 0.0)) { fx_set_error("kpca_fit: eps must be >= 0"); return -11; }
+    if (!V) { fx_set_error("kpca_fit: V is NULL"); return -13; }
+    if (ldv < n) { fx_set_error("kpca_fit: ldv < n (DimensionMismatch)"); return -14; }
+    if (!lambda) { fx_set_error("kpca_fit: lambda is NULL"); return -15; }
+
+    FX_CUDA(cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    fx_solver_opts o;
+    fx_resolve_opts(opts, k, &o);
+    const int G = ctx->world;
+    const int64_t ld = round_up(ceil_div(n, G), 128), n_ld = ld * G;
+    const int64_t row0 = ld * ctx->rank;
+    int64_t rows_valid = n - row0;
+    if (rows_valid < 0) rows_valid = 0;
+    if (rows_valid > ld) rows_valid = ld;
+    const int64_t d_pad = round_up(d, 16);
+    const int kp = (int)round_up(k, 8);
+    const bool dense = (n <= 256) || (k > 64) || (n < 8 * (int64_t)o.block);
+    if (dense && n > 1024) {
+        fx_set_error("kpca_fit: k=%d > 64 components is only supported for n <= 1024 (dense path)", k);
+        return -8;
+    }
+    if (!dense) {
+        int64_t mb = n / (2 * o.block) - 1;
+        if (mb < 2) mb = 2;
+        if (o.max_blocks > mb) o.max_blocks = (int)mb;
+    }
+
+    size_t need = fx_gramstage_bytes(ld, n_ld, d_pad, center != 0);
+    need += fx_align256((size_t)kp * n_ld * 8) + fx_align256((size_t)(kp + 8) * 8) + 4096;
+    if (dense) need += 3 * fx_align256((size_t)n * n * 8) + fx_align256((size_t)n_ld * n_ld * 8) + 8192;
+    else need += fx_eig_workspace_bytes(ctx, ld, n_ld, k, o);
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+
+    TotalTimer tot;
+    FX_TRY(tot.start(ctx));
+    FxTimer tm(ctx);
+    cudaStream_t s = ctx->stream;
+
+    GramStage g;
+    g.n = n; g.d = d; g.ld = ld; g.n_ld = n_ld; g.d_pad = d_pad; g.row0 = row0; g.rows_valid = rows_valid;
+    FX_TRY(fx_gramstage_run(ctx, g, X, on_dev, ldx, kernel_id, kpv, center != 0, o.variant, tm, st));
+
+    double* Vout = (double*)fx_arena_alloc(ctx, (size_t)kp * n_ld * 8);
+    double* theta = (double*)fx_arena_alloc(ctx, (size_t)(kp + 8) * 8);
+    if (!Vout || !theta) { fx_set_error("internal: arena too small"); return FX_ERR_OOM; }
+
+    EigArgs ea;
+    ea.K = g.K; ea.ldk = n_ld; ea.n = n; ea.ld = ld; ea.n_ld = n_ld; ea.row0 = row0;
+    ea.rows_valid = rows_valid; ea.k = k; ea.opts = o; ea.Vout = Vout; ea.theta = theta;
+    tm.begin(&st->eig_ms);
+    int eig_rc = dense ? fx_eig_dense(ctx, ea, tm, st) : fx_eig_topk(ctx, ea, tm, st);
+    tm.end();
+    if (eig_rc != 0 && eig_rc != FX_ERR_NOT_CONVERGED) return eig_rc;
+
+    // eigenvalue post-process: regularize!/perturb! (kpca.jl:53-54) only remap the spectrum,
+    // lambda' = ((1-alpha) theta + alpha tr(K~)/n + eps (n-1)) / (n-1)   (kpca.jl:56)
+    double* hp = ctx->pinned + 128;
+    FX_CUDA(cudaMemcpyAsync(hp, theta, k * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(hp + 64 + 8, g.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    const double trace = hp[64 + 8 + 1];
+    st->trace = trace;
+    std::vector<double> lam(k);
+    for (int i = 0; i < k; ++i)
+        lam[i] = ((1.0 - alpha) * hp[i] + alpha * trace / (double)n + eps * (double)(n - 1)) / (double)(n - 1);
+    tm.begin(&st->d2h_ms);
+    if (on_dev) {
+        for (int i = 0; i < k; ++i) hp[i] = lam[i];
+        FX_CUDA(cudaMemcpyAsync(lambda, hp, k * sizeof(double), cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaMemcpy2DAsync(V, ldv * 8, Vout, n_ld * 8, n * 8, k, cudaMemcpyDeviceToDevice, s));
+    } else {
+        for (int i = 0; i < k; ++i) lambda[i] = lam[i];
+        FX_CUDA(cudaMemcpy2DAsync(V, ldv * 8, Vout, n_ld * 8, n * 8, k, cudaMemcpyDeviceToHost, s));
+        st->d2h_bytes += n * k * 8 + k * 8;
+    }
+    tm.end();
+    if (model) FX_TRY(fx_model_build(ctx, g, kernel_id, kpv, k, Vout, center != 0, false, model));
+    FX_TRY(tot.stop(ctx, &st->total_ms));
+    tm.resolve();
+    st->kernel_launches = ctx->launches - launches0;
+    return eig_rc;
+}
+
+extern "C" int fx_kpca_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx,
+                               int kernel_id, const double* kparams, int k, int center, double alpha,
+                               double eps, const fx_solver_opts* opts, double* V, int64_t ldv,
+                               double* lambda, fx_model** model, fx_stats* stats) {
+    return kpca_fit_impl(ctx, X, false, n, d, ldx, kernel_id, kparams, k, center, alpha, eps, opts, V,
+                         ldv, lambda, model, stats);
+}
+
+extern "C" int fx_kpca_fit_dev_f64(fx_ctx* ctx, const double* dX, int64_t n, int64_t d, int64_t ldx,
+                                   int kernel_id, const double* kparams, int k, int center,
+                                   double alpha, double eps, const fx_solver_opts* opts, double* dV,
+                                   int64_t ldv, double* dlambda, fx_model** model, fx_stats* stats) {
+    return kpca_fit_impl(ctx, dX, true, n, d, ldx, kernel_id, kparams, k, center, alpha, eps, opts, dV,
+                         ldv, dlambda, model, stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// building blocks
+// ---------------------------------------------------------------------------------------------
+extern "C" int fx_gram_f64(fx_ctx* ctx, const double* Z, int64_t m, int64_t ldz, const double* X,
+                           int64_t n, int64_t ldx, int64_t d, int kernel_id, const double* kparams,
+                           int variant, double* K, int64_t ldk, fx_stats* stats) {
+    fx_stats local;
+    fx_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!ctx) return -1;
+    const bool sym = (Z == nullptr);
+    if (sym) { m = n; }
+    if (m < 1) return -2;
+    if (!sym && ldz < m) return -3;
+    if (!X) return -4;
+    if (n < 1) return -5;
+    if (ldx < n) return -6;
+    if (d < 1) return -7;
+    double kpv[3]; int ipow;
+    if (!kparams || fx_make_kernel_map(kernel_id, kparams, &ipow, kpv)) {
+        fx_set_error("gram: unknown kernel id or invalid parameters");
+        return -8;
+    }
+    if (!K) return -11;
+    if (ldk < m) return -12;
+    FX_CUDA(cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    // device result is row-major [n_pad][m_ld] = column-major m x n with leading dimension m_ld
+    const int64_t n_pad = round_up(n, 128), m_ld = round_up(m, 128), d_pad = round_up(d, 16);
+    size_t need = fx_align256((size_t)d_pad * n_pad * 8) + fx_align256((size_t)d_pad * m_ld * 8) +
+                  fx_align256((size_t)n_pad * 8) + fx_align256((size_t)m_ld * 8) +
+                  fx_align256((size_t)n_pad * m_ld * 8) + 8192;
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+    cudaStream_t s = ctx->stream;
+    double* Xp = (double*)fx_arena_alloc(ctx, (size_t)d_pad * n_pad * 8);
+    double* Zp = sym ? Xp : (double*)fx_arena_alloc(ctx, (size_t)d_pad * m_ld * 8);
+    double* nx = (double*)fx_arena_alloc(ctx, (size_t)n_pad * 8);
+    double* nz = sym ? nx : (double*)fx_arena_alloc(ctx, (size_t)m_ld * 8);
+    double* Kd = (double*)fx_arena_alloc(ctx, (size_t)n_pad * m_ld * 8);
+    TotalTimer tot;
+    FX_TRY(tot.start(ctx));
+    FxTimer tm(ctx);
+    FX_CUDA(cudaMemsetAsync(Xp, 0, (size_t)d_pad * n_pad * 8, s));
+    FX_CUDA(cudaMemcpy2DAsync(Xp, n_pad * 8, X, ldx * 8, n * 8, d, cudaMemcpyHostToDevice, s));
+    FX_TRY(fx_launch_rownorms(ctx, Xp, n_pad, n_pad, d_pad, nx));
+    if (!sym) {
+        FX_CUDA(cudaMemsetAsync(Zp, 0, (size_t)d_pad * m_ld * 8, s));
+        FX_CUDA(cudaMemcpy2DAsync(Zp, m_ld * 8, Z, ldz * 8, m * 8, d, cudaMemcpyHostToDevice, s));
+        FX_TRY(fx_launch_rownorms(ctx, Zp, m_ld, m_ld, d_pad, nz));
+    }
+    GramArgs ga;
+    ga.A = Xp; ga.lda = n_pad; ga.B = Zp; ga.ldb = sym ? n_pad : m_ld; ga.na = nx; ga.nb = nz;
+    ga.d_pad = d_pad; ga.K = Kd; ga.ldk = m_ld; ga.rows_pad = n_pad; ga.rows_valid = n;
+    ga.cols_valid = m; ga.diag_shift = sym ? 0 : -1; ga.rowpart = nullptr;
+    ga.kernel_id = kernel_id; ga.kp[0] = kpv[0]; ga.kp[1] = kpv[1]; ga.kp[2] = kpv[2];
+    tm.begin(&st->gram_ms);
+    FX_TRY(fx_launch_gram(ctx, ga, variant));
+    tm.end();
+    st->gram_launches = 1;
+    FX_CUDA(cudaMemcpy2DAsync(K, ldk * 8, Kd, m_ld * 8, m * 8, n, cudaMemcpyDeviceToHost, s));
+    FX_TRY(tot.stop(ctx, &st->total_ms));
+    tm.resolve();
+    st->kernel_launches = ctx->launches - launches0;
+    return 0;
+}
+
+extern "C" int fx_center_f64(fx_ctx* ctx, double* K, int64_t n, int64_t ldk, double* colmean,
+                             double* grandmean, fx_stats* stats) {
+    fx_stats local;
+    fx_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!ctx) return -1;
+    if (!K) return -2;
+    if (n < 1) return -3;
+    if (ldk < n) { fx_set_error("center: ldk < n (DimensionMismatch)"); return -4; }
+    FX_CUDA(cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    const int64_t n_ld = round_up(n, 64);
+    size_t need = fx_align256((size_t)n * n_ld * 8) + 3 * fx_align256((size_t)n_ld * 8) + 8192;
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+    cudaStream_t s = ctx->stream;
+    double* Kd = (double*)fx_arena_alloc(ctx, (size_t)n * n_ld * 8);
+    double* rs = (double*)fx_arena_alloc(ctx, (size_t)n_ld * 8);
+    double* cm = (double*)fx_arena_alloc(ctx, (size_t)n_ld * 8);
+    double* sc = (double*)fx_arena_alloc(ctx, 256);
+    TotalTimer tot;
+    FX_TRY(tot.start(ctx));
+    FxTimer tm(ctx);
+    FX_CUDA(cudaMemsetAsync(Kd, 0, (size_t)n * n_ld * 8, s));
+    FX_CUDA(cudaMemcpy2DAsync(Kd, n_ld * 8, K, ldk * 8, n * 8, n, cudaMemcpyHostToDevice, s));
+    tm.begin(&st->center_ms);
+    FX_TRY(fx_launch_rowsums(ctx, Kd, n_ld, n, n, rs));
+    FX_TRY(fx_launch_means(ctx, rs, n, n_ld, cm, sc));
+    FX_TRY(fx_launch_center(ctx, Kd, n_ld, n, n, 0, cm, sc));
+    tm.end();
+    st->center_launches = 1;
+    FX_CUDA(cudaMemcpy2DAsync(K, ldk * 8, Kd, n_ld * 8, n * 8, n, cudaMemcpyDeviceToHost, s));
+    if (colmean) FX_CUDA(cudaMemcpyAsync(colmean, cm, n * 8, cudaMemcpyDeviceToHost, s));
+    if (grandmean) FX_CUDA(cudaMemcpyAsync(grandmean, sc, 8, cudaMemcpyDeviceToHost, s));
+    FX_TRY(tot.stop(ctx, &st->total_ms));
+    tm.resolve();
+    st->kernel_launches = ctx->launches - launches0;
+    return 0;
+}
+
+extern "C" int fx_symm_f64(fx_ctx* ctx, const double* K, int64_t n, int64_t ldk, const double* V, int b,
+                           int64_t ldv, double* Y, int64_t ldy, int variant, fx_stats* stats) {
+    fx_stats local;
+    fx_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!ctx) return -1;
+    if (!K) return -2;
+    if (n < 1) return -3;
+    if (ldk < n) return -4;
+    if (!V) return -5;
+    if (b < 1 || b > 64) { fx_set_error("symm: block width must be 1..64"); return -6; }
+    if (ldv < n) return -7;
+    if (!Y) return -8;
+    if (ldy < n) return -9;
+    FX_CUDA(cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    const int64_t np = round_up(n, 128);
+    const int bp = (int)round_up(b, 8);
+    const int splits = fx_symm_splits(ctx, np, np);
+    size_t need = fx_align256((size_t)np * np * 8) + 2 * fx_align256((size_t)bp * np * 8) +
+                  fx_align256((size_t)splits * bp * np * 8) + 8192;
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+    cudaStream_t s = ctx->stream;
+    double* Kd = (double*)fx_arena_alloc(ctx, (size_t)np * np * 8);
+    double* Vd = (double*)fx_arena_alloc(ctx, (size_t)bp * np * 8);
+    double* Yd = (double*)fx_arena_alloc(ctx, (size_t)bp * np * 8);
+    double* Yp = (double*)fx_arena_alloc(ctx, (size_t)splits * bp * np * 8);
+    TotalTimer tot;
+    FX_TRY(tot.start(ctx));
+    FxTimer tm(ctx);
+    FX_CUDA(cudaMemsetAsync(Kd, 0, (size_t)np * np * 8, s));
+    FX_CUDA(cudaMemsetAsync(Vd, 0, (size_t)bp * np * 8, s));
+    FX_CUDA(cudaMemcpy2DAsync(Kd, np * 8, K, ldk * 8, n * 8, n, cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemcpy2DAsync(Vd, np * 8, V, ldv * 8, n * 8, b, cudaMemcpyHostToDevice, s));
+    SymmArgs sa;
+    sa.K = Kd; sa.ldk = np; sa.rows_pad = np; sa.V = Vd; sa.ldr = np; sa.v_rank_stride = (int64_t)bp * np;
+    sa.bcols = bp; sa.Y = Yd; sa.Ypart = Yp; sa.splits = splits;
+    tm.begin(&st->symm_ms);
+    FX_TRY(fx_launch_symm(ctx, sa, variant));
+    tm.end();
+    st->symm_launches = 1;
+    FX_CUDA(cudaMemcpy2DAsync(Y, ldy * 8, Yd, np * 8, n * 8, b, cudaMemcpyDeviceToHost, s));
+    FX_TRY(tot.stop(ctx, &st->total_ms));
+    tm.resolve();
+    st->kernel_launches = ctx->launches - launches0;
+    return 0;
+}
+
+extern "C" int fx_syevd_small_f64(fx_ctx* ctx, double* A, int m, int64_t lda, double* w, int* sweeps) {
+    if (!ctx) return -1;
+    if (!A) return -2;
+    if (m < 1 || m > 1024) { fx_set_error("syevd_small: order must be 1..1024"); return -3; }
+    if (lda < m) { fx_set_error("syevd_small: lda < m (DimensionMismatch)"); return -4; }
+    if (!w) return -5;
+    FX_CUDA(cudaSetDevice(ctx->device));
+    size_t need = 3 * fx_align256((size_t)m * m * 8) + fx_align256((size_t)m * 8) + 8192;
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+    cudaStream_t s = ctx->stream;
+    double* Ad = (double*)fx_arena_alloc(ctx, (size_t)m * m * 8);
+    double* Sd = (double*)fx_arena_alloc(ctx, (size_t)m * m * 8);
+    double* Wk = (double*)fx_arena_alloc(ctx, (size_t)m * m * 8);
+    double* wd = (double*)fx_arena_alloc(ctx, (size_t)m * 8);
+    int* info = (int*)fx_arena_alloc(ctx, 64);
+    FX_CUDA(cudaMemcpy2DAsync(Ad, (size_t)m * 8, A, lda * 8, (size_t)m * 8, m, cudaMemcpyHostToDevice, s));
+    FX_TRY(fx_launch_jacobi(ctx, Ad, m, m, Sd, m, wd, Wk, info));
+    FX_CUDA(cudaMemcpy2DAsync(A, lda * 8, Sd, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(w, wd, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
+    int hinfo[2] = {0, 0};
+    FX_CUDA(cudaMemcpyAsync(hinfo, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    if (sweeps) *sweeps = hinfo[0];
+    if (!hinfo[1]) { fx_set_error("syevd_small: Jacobi did not converge"); return FX_ERR_NOT_CONVERGED; }
+    return 0;
+}

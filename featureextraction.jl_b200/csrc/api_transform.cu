@@ -1,0 +1,178 @@
+// api_transform.cu -- C ABI: out-of-sample projection (transform_kpca, kpca.jl:64-68;
+// transform_klda, klda.jl:71) through the fused kernel of transform.cu, and the stateless
+// model constructor that serves the reference's signature transform_kpca(X, k, W, Z).
+#include "fx_kernels.cuh"
+
+namespace {
+constexpr int64_t QCHUNK = 131072;      // queries per launch (bounds device scratch)
+
+int transform_impl(fx_ctx* ctx, const fx_model* md, const double* Z, bool on_dev, int64_t m,
+                   int64_t ldz, double* out, int64_t ldo, fx_stats* stats, int variant) {
+    fx_stats local;
+    fx_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!ctx) return -1;
+    if (!md) { fx_set_error("transform: model is NULL"); return -2; }
+    if (!Z) return -3;
+    if (m < 1) return -4;
+    if (ldz < m) { fx_set_error("transform: ldz < m (DimensionMismatch)"); return -5; }
+    if (!out) return -6;
+    if (ldo < m) { fx_set_error("transform: ldo < m (DimensionMismatch)"); return -7; }
+    if (md->device != ctx->device) { fx_set_error("transform: model lives on another device"); return -2; }
+    FX_CUDA(cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    const int kc = md->k_pad;
+    const int64_t mc_max = m < QCHUNK ? round_up(m, 128) : QCHUNK;
+    int nsplit = 1;
+    const size_t scr = fx_transform_scratch(ctx, mc_max, md->n_ld, kc, &nsplit);
+    size_t need = fx_align256((size_t)md->d_pad * mc_max * 8) + fx_align256((size_t)mc_max * 8) +
+                  fx_align256((size_t)kc * mc_max * 8) + fx_align256(scr * 8) + 8192;
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+    cudaStream_t s = ctx->stream;
+    double* Zp = (double*)fx_arena_alloc(ctx, (size_t)md->d_pad * mc_max * 8);
+    double* nz = (double*)fx_arena_alloc(ctx, (size_t)mc_max * 8);
+    double* od = (double*)fx_arena_alloc(ctx, (size_t)kc * mc_max * 8);
+    double* scratch = scr ? (double*)fx_arena_alloc(ctx, scr * 8) : nullptr;
+
+    cudaEvent_t e0, e1;
+    FX_CUDA(cudaEventCreate(&e0));
+    FX_CUDA(cudaEventCreate(&e1));
+    FX_CUDA(cudaEventRecord(e0, s));
+    FxTimer tm(ctx);
+    for (int64_t q0 = 0; q0 < m; q0 += QCHUNK) {
+        const int64_t mc = (m - q0) < QCHUNK ? (m - q0) : QCHUNK;
+        const int64_t mp = round_up(mc, 128);
+        int ns = 1;
+        fx_transform_scratch(ctx, mp, md->n_ld, kc, &ns);
+        if (ns > nsplit) ns = nsplit;
+        tm.begin(&st->h2d_ms);
+        FX_CUDA(cudaMemsetAsync(Zp, 0, (size_t)md->d_pad * mp * 8, s));
+        FX_CUDA(cudaMemcpy2DAsync(Zp, mp * 8, Z + q0, ldz * 8, mc * 8, md->d,
+                                  on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        tm.end();
+        if (!on_dev) st->h2d_bytes += mc * md->d * 8;
+        FX_TRY(fx_launch_rownorms(ctx, Zp, mp, mp, md->d_pad, nz));
+        TransformArgs ta;
+        ta.Zp = Zp; ta.ldz = mp; ta.nz = nz; ta.Xp = md->Xp; ta.ldx = md->n_ld; ta.nx = md->norms;
+        ta.d_pad = md->d_pad; ta.m_pad = mp; ta.n_ld = md->n_ld; ta.n_valid = md->n;
+        ta.W = md->W; ta.ldw = md->n_ld; ta.kcols = kc; ta.bias = md->centered ? md->bias : nullptr;
+        ta.out = od; ta.ldo = mp; ta.kernel_id = md->kernel_id;
+        ta.kp[0] = md->kp[0]; ta.kp[1] = md->kp[1]; ta.kp[2] = md->kp[2];
+        tm.begin(&st->transform_ms);
+        FX_TRY(fx_launch_transform_ex(ctx, ta, variant, scratch, ns));
+        tm.end();
+        st->transform_launches++;
+        tm.begin(&st->d2h_ms);
+        FX_CUDA(cudaMemcpy2DAsync(out + q0, ldo * 8, od, mp * 8, mc * 8, md->k,
+                                  on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        tm.end();
+        if (!on_dev) st->d2h_bytes += mc * md->k * 8;
+    }
+    FX_CUDA(cudaEventRecord(e1, s));
+    FX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    st->total_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    tm.resolve();
+    st->kernel_launches = ctx->launches - launches0;
+    return 0;
+}
+}  // namespace
+
+extern "C" int fx_kpca_transform_f64(fx_ctx* ctx, const fx_model* model, const double* Z, int64_t m,
+                                     int64_t ldz, double* out, int64_t ldo, fx_stats* stats) {
+    return transform_impl(ctx, model, Z, false, m, ldz, out, ldo, stats, 0);
+}
+extern "C" int fx_kpca_transform_dev_f64(fx_ctx* ctx, const fx_model* model, const double* dZ, int64_t m,
+                                         int64_t ldz, double* dout, int64_t ldo, fx_stats* stats) {
+    return transform_impl(ctx, model, dZ, true, m, ldz, dout, ldo, stats, 0);
+}
+extern "C" int fx_klda_transform_f64(fx_ctx* ctx, const fx_model* model, const double* Z, int64_t m,
+                                     int64_t ldz, double* out, int64_t ldo, fx_stats* stats) {
+    return transform_impl(ctx, model, Z, false, m, ldz, out, ldo, stats, 0);
+}
+// debug / parity: same call through the naive CUDA kernel
+extern "C" int fx_kpca_transform_naive_f64(fx_ctx* ctx, const fx_model* model, const double* Z, int64_t m,
+                                           int64_t ldz, double* out, int64_t ldo, fx_stats* stats) {
+    return transform_impl(ctx, model, Z, false, m, ldz, out, ldo, stats, 1);
+}
+
+extern "C" int fx_model_create_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx,
+                                   int kernel_id, const double* kparams, const double* W, int k,
+                                   int64_t ldw, int center, fx_model** model, fx_stats* stats) {
+    fx_stats local;
+    fx_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!ctx) return -1;
+    if (!X) return -2;
+    if (n < 1) return -3;
+    if (d < 1) return -4;
+    if (ldx < n) { fx_set_error("model_create: ldx < n (DimensionMismatch)"); return -5; }
+    double kpv[3]; int ipow;
+    if (!kparams || fx_make_kernel_map(kernel_id, kparams, &ipow, kpv)) {
+        fx_set_error("model_create: unknown kernel id or invalid parameters");
+        return -6;
+    }
+    if (!W) return -8;
+    if (k < 1 || k > 64) { fx_set_error("model_create: k must be 1..64"); return -9; }
+    if (ldw < n) { fx_set_error("model_create: ldw < n (DimensionMismatch: W must have n rows)"); return -10; }
+    if (!model) return -12;
+    *model = nullptr;
+    FX_CUDA(cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    cudaStream_t s = ctx->stream;
+    const int64_t n_ld = round_up(n, 128), d_pad = round_up(d, 16);
+    const int kc = (int)round_up(k, 8);
+    fx_model* m = new fx_model();
+    m->device = ctx->device; m->n = n; m->d = d; m->n_ld = n_ld; m->d_pad = d_pad; m->k = k; m->k_pad = kc;
+    m->kernel_id = kernel_id; m->kp[0] = kpv[0]; m->kp[1] = kpv[1]; m->kp[2] = kpv[2];
+    m->centered = center ? 1 : 0;
+    auto fail = [&](int rc) { fx_model_free(m); return rc; };
+    if (cudaMalloc((void**)&m->Xp, (size_t)d_pad * n_ld * 8) != cudaSuccess ||
+        cudaMalloc((void**)&m->norms, (size_t)n_ld * 8) != cudaSuccess ||
+        cudaMalloc((void**)&m->W, (size_t)kc * n_ld * 8) != cudaSuccess ||
+        cudaMalloc((void**)&m->bias, 64 * 8) != cudaSuccess ||
+        cudaMalloc((void**)&m->colmean, (size_t)n_ld * 8) != cudaSuccess) {
+        cudaGetLastError();
+        fx_set_error("model_create: out of device memory");
+        return fail(FX_ERR_OOM);
+    }
+    int rc = 0;
+#define MC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fx_set_error("CUDA error %s (%s)", cudaGetErrorString(_e), #expr); return fail(FX_ERR_CUDA); } } while (0)
+    MC(cudaMemsetAsync(m->Xp, 0, (size_t)d_pad * n_ld * 8, s));
+    MC(cudaMemcpy2DAsync(m->Xp, n_ld * 8, X, ldx * 8, n * 8, d, cudaMemcpyHostToDevice, s));
+    MC(cudaMemsetAsync(m->W, 0, (size_t)kc * n_ld * 8, s));
+    MC(cudaMemcpy2DAsync(m->W, n_ld * 8, W, ldw * 8, n * 8, k, cudaMemcpyHostToDevice, s));
+    MC(cudaMemsetAsync(m->bias, 0, 64 * 8, s));
+    MC(cudaMemsetAsync(m->colmean, 0, (size_t)n_ld * 8, s));
+    if ((rc = fx_launch_rownorms(ctx, m->Xp, n_ld, n_ld, d_pad, m->norms))) return fail(rc);
+    st->h2d_bytes = n * d * 8 + n * k * 8;
+    if (center) {
+        // bias = r'W = (1/n) 1' K W = column means of the uncentred in-sample projection
+        int nsplit = 1;
+        const size_t scr = fx_transform_scratch(ctx, n_ld, n_ld, kc, &nsplit);
+        size_t need = 2 * fx_align256((size_t)kc * n_ld * 8) + fx_align256(scr * 8) + fx_align256((size_t)n_ld * 8) + 8192;
+        if ((rc = fx_arena_reserve(ctx, need))) return fail(rc);
+        fx_arena_reset(ctx);
+        double* T = (double*)fx_arena_alloc(ctx, (size_t)kc * n_ld * 8);
+        double* ones = (double*)fx_arena_alloc(ctx, (size_t)n_ld * 8);
+        double* scratch = scr ? (double*)fx_arena_alloc(ctx, scr * 8) : nullptr;
+        TransformArgs ta;
+        ta.Zp = m->Xp; ta.ldz = n_ld; ta.nz = m->norms; ta.Xp = m->Xp; ta.ldx = n_ld; ta.nx = m->norms;
+        ta.d_pad = d_pad; ta.m_pad = n_ld; ta.n_ld = n_ld; ta.n_valid = n; ta.W = m->W; ta.ldw = n_ld;
+        ta.kcols = kc; ta.bias = nullptr; ta.out = T; ta.ldo = n_ld; ta.kernel_id = kernel_id;
+        ta.kp[0] = kpv[0]; ta.kp[1] = kpv[1]; ta.kp[2] = kpv[2];
+        if ((rc = fx_launch_transform_ex(ctx, ta, 0, scratch, nsplit))) return fail(rc);
+        st->transform_launches = 1;
+        if ((rc = fx_launch_fill(ctx, ones, n_ld, 1.0 / (double)n))) return fail(rc);
+        if ((rc = fx_launch_bias(ctx, ones, T, n_ld, n, kc, m->bias))) return fail(rc);
+    }
+    MC(cudaStreamSynchronize(s));
+#undef MC
+    st->kernel_launches = ctx->launches - launches0;
+    *model = m;
+    return 0;
+}

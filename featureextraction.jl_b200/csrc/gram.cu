@@ -1,0 +1,220 @@
+// gram.cu -- kernel-matrix construction: K = map(A B') with the kernel map, zero padding and
+// per-tile row sums fused into the epilogue.  Replaces MLKernels.kernelmatrix as called at
+// /root/reference/src/kpca.jl:51 (symmetric) and kpca.jl:65 (cross).
+//
+// Data path (per 128x64 output tile, 4 warps, 2 CTAs/SM):
+//   HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier--> 4-stage smem ring of 16-feature
+//   slabs --LDS.64 conflict-free (row stride = 4 mod 16 doubles)--> DMMA.8x8x4 (mma.sync f64)
+//   64x32 register tile per warp --> smem staging --> kernel map + warp-shuffle row sums
+//   --> 16-byte coalesced stores (a warp writes 512 contiguous bytes of one K row).
+#include "fx_kernels.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
+constexpr int AS = BM + 4;                      // 132: (t*AS + g) mod 16 distinct for t,g in 0..3
+constexpr int BS = BN + 4;                      // 68
+constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25600 B)
+constexpr int CS = 72;                          // staging row stride (conflict-free STS.128)
+constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 64;
+static_assert(BM * CS <= STAGES * STAGE_D, "staging tile must fit in the pipeline buffers");
+
+struct GramParams {
+    const double* A; long lda;
+    const double* B; long ldb;
+    const double* na; const double* nb;
+    double* K; long ldk;
+    double* rowpart; long rows_pad;
+    long rows_valid, cols_valid, diag_shift;
+    int kt;
+    KernelMap km;
+};
+
+__global__ void __launch_bounds__(128, 2) gram_dmma_kernel(const GramParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_D * 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const long i0 = (long)blockIdx.y * BM;
+    const long j0 = (long)blockIdx.x * BN;
+    const int KT = p.kt;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int kt, int s) {           // all 32 lanes of warp 0
+        double* As = smem + (size_t)s * STAGE_D;
+        double* Bs = As + BK * AS;
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], BK * (BM + BN) * 8);
+        __syncwarp();
+        if (lane < BK)
+            bulk_g2s(As + lane * AS, p.A + (long)(kt * BK + lane) * p.lda + i0, BM * 8, &full[s]);
+        else
+            bulk_g2s(Bs + (lane - BK) * BS, p.B + (long)(kt * BK + lane - BK) * p.ldb + j0, BN * 8,
+                     &full[s]);
+    };
+    if (warp == 0)
+        for (int s = 0; s < STAGES && s < KT; ++s) issue(s, s);
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % STAGES;
+        mbar_wait(&full[s], (kt / STAGES) & 1);
+        const double* As = smem + (size_t)s * STAGE_D + wm * 64 + g;
+        const double* Bs = smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[8], b[4];
+            const int kr = kk * 4 + t;
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * AS + mt * 8];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * BS + nt * 8];
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        }
+        __syncthreads();                         // every warp is done with stage s
+        if (warp == 0 && kt + STAGES < KT) issue(kt + STAGES, s);
+    }
+
+    // ---- epilogue: registers -> smem staging tile -> map + row sums -> coalesced stores ----
+    double* Cs = smem;                           // all bulk copies have landed and been consumed
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int r = wm * 64 + mt * 8 + g, c = wn * 32 + nt * 8 + 2 * t;
+            *reinterpret_cast<double2*>(&Cs[r * CS + c]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        }
+    __syncthreads();
+
+    const long j = j0 + 2 * lane;
+    const bool jv0 = j < p.cols_valid, jv1 = (j + 1) < p.cols_valid;
+    double nb0 = 0.0, nb1 = 0.0;
+    if (p.km.id == FX_KERNEL_GAUSSIAN) {
+        nb0 = p.nb[j];
+        nb1 = p.nb[j + 1];
+    }
+    const int jt = blockIdx.x;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+        const int r = warp * 32 + rr;
+        const long i = i0 + r;
+        const double2 dot = *reinterpret_cast<const double2*>(&Cs[r * CS + 2 * lane]);
+        double v0 = 0.0, v1 = 0.0;
+        if (i < p.rows_valid) {
+            const double ni = (p.km.id == FX_KERNEL_GAUSSIAN) ? p.na[i] : 0.0;
+            const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+            if (jv0) v0 = kernel_map(p.km, dot.x, ni, nb0, ig == j);
+            if (jv1) v1 = kernel_map(p.km, dot.y, ni, nb1, ig == j + 1);
+        }
+        *reinterpret_cast<double2*>(&p.K[i * p.ldk + j]) = make_double2(v0, v1);
+        if (p.rowpart) {
+            const double s = warp_sum(v0 + v1);
+            if (lane == 0) p.rowpart[(long)jt * p.rows_pad + i] = s;
+        }
+    }
+}
+
+// ---- naive cross-check variant: one thread per output element -------------------------------
+__global__ void gram_naive_kernel(const GramParams p, int d_pad) {
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long i = blockIdx.y;
+    if (j >= p.ldk) return;
+    double v = 0.0;
+    if (i < p.rows_valid && j < p.cols_valid) {
+        double dot = 0.0;
+        for (int f = 0; f < d_pad; ++f) dot += p.A[(long)f * p.lda + i] * p.B[(long)f * p.ldb + j];
+        const double ni = (p.km.id == FX_KERNEL_GAUSSIAN) ? p.na[i] : 0.0;
+        const double nj = (p.km.id == FX_KERNEL_GAUSSIAN) ? p.nb[j] : 0.0;
+        const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+        v = kernel_map(p.km, dot, ni, nj, ig == j);
+    }
+    p.K[i * p.ldk + j] = v;
+}
+// naive per-tile row sums so both variants feed the same reduction
+__global__ void gram_naive_rowpart_kernel(const double* K, long ldk, double* rowpart, long rows_pad) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long jt = blockIdx.y;
+    if (i >= rows_pad) return;
+    double s = 0.0;
+    for (int c = 0; c < 64; ++c) s += K[i * ldk + jt * 64 + c];
+    rowpart[jt * rows_pad + i] = s;
+}
+
+__global__ void rownorms_kernel(const double* P, long ld, long nobs, int d_pad, double* norms) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nobs) return;
+    double s = 0.0;
+    for (int f = 0; f < d_pad; ++f) {
+        const double x = P[(long)f * ld + i];
+        s = fma(x, x, s);
+    }
+    norms[i] = s;
+}
+
+}  // namespace
+
+int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, int64_t d_pad,
+                       double* norms) {
+    if (nobs <= 0) return 0;
+    rownorms_kernel<<<(unsigned)ceil_div(nobs, 256), 256, 0, ctx->stream>>>(P, ld, nobs, (int)d_pad, norms);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
+    if (a.rows_pad % BM || a.ldk % BN || a.d_pad % BK || a.lda % 2 || a.ldb % 2) {
+        fx_set_error("gram: bad padding rows_pad=%lld ldk=%lld d_pad=%lld", (long long)a.rows_pad,
+                     (long long)a.ldk, (long long)a.d_pad);
+        return FX_ERR_CUDA;
+    }
+    GramParams p;
+    p.A = a.A; p.lda = a.lda; p.B = a.B; p.ldb = a.ldb; p.na = a.na; p.nb = a.nb;
+    p.K = a.K; p.ldk = a.ldk; p.rowpart = a.rowpart; p.rows_pad = a.rows_pad;
+    p.rows_valid = a.rows_valid; p.cols_valid = a.cols_valid; p.diag_shift = a.diag_shift;
+    p.kt = (int)(a.d_pad / BK);
+    p.km.id = a.kernel_id; p.km.p0 = a.kp[0]; p.km.p1 = a.kp[1]; p.km.p2 = a.kp[2];
+    double tmp[3];
+    if (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp)) {
+        fx_set_error("gram: invalid kernel id / parameters");
+        return -1;
+    }
+    if (a.rows_pad == 0 || a.ldk == 0) return 0;
+    if (variant == 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            attr_set = true;
+        }
+        dim3 grid((unsigned)(a.ldk / BN), (unsigned)(a.rows_pad / BM));
+        gram_dmma_kernel<<<grid, 128, SMEM_BYTES, ctx->stream>>>(p);
+        ctx->launches++;
+    } else {
+        dim3 grid((unsigned)ceil_div(a.ldk, 256), (unsigned)a.rows_pad);
+        gram_naive_kernel<<<grid, 256, 0, ctx->stream>>>(p, (int)a.d_pad);
+        ctx->launches++;
+        if (a.rowpart) {
+            dim3 g2((unsigned)ceil_div(a.rows_pad, 256), (unsigned)(a.ldk / 64));
+            gram_naive_rowpart_kernel<<<g2, 256, 0, ctx->stream>>>(a.K, a.ldk, a.rowpart, a.rows_pad);
+            ctx->launches++;
+        }
+    }
+    FX_LAUNCH_CHECK();
+    return 0;
+}

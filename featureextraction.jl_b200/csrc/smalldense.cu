@@ -1,0 +1,398 @@
+// smalldense.cu -- the small dense pieces of the eigensolver, all on the device:
+//   * parallel cyclic Jacobi eigensolver (Rayleigh-Ritz on the projected matrix T and the
+//     b x b Gram matrices of the SVQB orthonormalisation); also the dense path for tiny n.
+//     This is what stands in for LAPACK dsyevd (/root/reference/src/common.jl:128-131) on the
+//     projected problem; descending order like components_eig! (common.jl:164).
+//   * SVQB factor construction, T bookkeeping, Ritz residuals, deterministic start block.
+// Single-CTA kernels: the matrices are at most a few hundred rows.
+#include "fx_kernels.cuh"
+
+namespace {
+
+constexpr int JT = 1024;                         // threads of the Jacobi CTA
+constexpr int J_SMEM_MAX_M = 160;                // A kept in shared memory up to this order
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        s = warp_sum(s);
+        if (threadIdx.x == 0) red[32] = s;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// Round-robin tournament: players 0..mp-1 (mp even), player mp-1 fixed.
+__device__ __forceinline__ void rr_pair(int rnd, int i, int mp, int& p, int& q) {
+    if (i == 0) {
+        p = mp - 1;
+        q = rnd;
+    } else {
+        p = (rnd + i) % (mp - 1);
+        q = (rnd - i + (mp - 1)) % (mp - 1);
+    }
+    if (p > q) { const int x = p; p = q; q = x; }
+}
+
+// A (m x m, lda) symmetric, destroyed.  V (m x m, ldv) receives the eigenvectors (unsorted),
+// then w / Vout the sorted (descending) results.
+__global__ void __launch_bounds__(JT, 1) jacobi_kernel(double* Ag, int lda_g, int m, double* V, int ldv,
+                                                       double* w, double* Vout, int ldvo, int* info,
+                                                       int use_smem, int max_sweeps) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[33];
+    __shared__ double rot_c[512], rot_s[512];
+    __shared__ int rot_p[512], rot_q[512];
+    __shared__ int s_rank[1024];
+    const int tid = threadIdx.x;
+    const int mp = m + (m & 1);
+    const int half = mp / 2;
+
+    double* A = Ag;
+    int lda = lda_g;
+    if (use_smem) {
+        lda = m | 1;                              // odd stride: conflict-free row access
+        A = sm;
+        for (int idx = tid; idx < m * m; idx += JT) {
+            const int i = idx % m, j = idx / m;
+            A[i + j * lda] = Ag[i + (long)j * lda_g];
+        }
+    }
+    for (int idx = tid; idx < m * m; idx += JT) {
+        const int i = idx % m, j = idx / m;
+        V[i + (long)j * ldv] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    int sweeps = 0, converged = 0;
+    double prev_off = 0.0;
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int idx = tid; idx < m * m; idx += JT) {
+            const int i = idx % m, j = idx / m;
+            const double a = A[i + j * lda];
+            if (i == j) dg += a * a; else off += a * a;
+        }
+        off = block_sum(off, red);
+        dg = block_sum(dg, red);
+        if (off <= 1e-30 * dg || off == 0.0) { converged = 1; break; }
+        // rounding floor reached: the off-diagonal norm stopped contracting
+        if (sweep > 2 && off > 0.25 * prev_off && off <= 1e-24 * dg) { converged = 1; break; }
+        prev_off = off;
+        sweeps++;
+        for (int rnd = 0; rnd < mp - 1; ++rnd) {
+            // phase 1: rotation parameters for the pairs of this round
+            for (int i = tid; i < half; i += JT) {
+                int pp, qq;
+                rr_pair(rnd, i, mp, pp, qq);
+                double c = 1.0, s = 0.0;
+                if (qq < m) {
+                    const double apq = A[pp + qq * lda];
+                    if (fabs(apq) > 1e-300) {
+                        const double tau = (A[qq + qq * lda] - A[pp + pp * lda]) / (2.0 * apq);
+                        const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + tt * tt);
+                        s = tt * c;
+                    }
+                } else {
+                    qq = -1;
+                }
+                rot_p[i] = pp; rot_q[i] = qq; rot_c[i] = c; rot_s[i] = s;
+            }
+            __syncthreads();
+            // phase 2: column rotations  A <- A J,  V <- V J
+            for (int idx = tid; idx < half * m; idx += JT) {
+                const int pr = idx / m, r = idx - pr * m;
+                const int pp = rot_p[pr], qq = rot_q[pr];
+                if (qq < 0) continue;
+                const double c = rot_c[pr], s = rot_s[pr];
+                if (s == 0.0) continue;
+                const double ap = A[r + pp * lda], aq = A[r + qq * lda];
+                A[r + pp * lda] = c * ap - s * aq;
+                A[r + qq * lda] = s * ap + c * aq;
+                const double vp = V[r + (long)pp * ldv], vq = V[r + (long)qq * ldv];
+                V[r + (long)pp * ldv] = c * vp - s * vq;
+                V[r + (long)qq * ldv] = s * vp + c * vq;
+            }
+            __syncthreads();
+            // phase 3: row rotations  A <- J' A
+            for (int idx = tid; idx < half * m; idx += JT) {
+                const int pr = idx / m, cc = idx - pr * m;
+                const int pp = rot_p[pr], qq = rot_q[pr];
+                if (qq < 0) continue;
+                const double c = rot_c[pr], s = rot_s[pr];
+                if (s == 0.0) continue;
+                const double ap = A[pp + cc * lda], aq = A[qq + cc * lda];
+                double np_ = c * ap - s * aq, nq_ = s * ap + c * aq;
+                if (cc == qq) np_ = 0.0;          // the annihilated pair, exactly
+                if (cc == pp) nq_ = 0.0;
+                A[pp + cc * lda] = np_;
+                A[qq + cc * lda] = nq_;
+            }
+            __syncthreads();
+        }
+    }
+    // sort descending by rank counting (stable), scatter eigenvectors
+    for (int i = tid; i < m; i += JT) {
+        const double di = A[i + i * lda];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) {
+            const double dj = A[j + j * lda];
+            rank += (dj > di) || (dj == di && j < i);
+        }
+        w[rank] = di;
+        s_rank[i] = rank;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < m * m; idx += JT) {
+        const int r = idx % m, i = idx / m;
+        Vout[r + (long)s_rank[i] * ldvo] = V[r + (long)i * ldv];
+    }
+    if (tid == 0 && info) { info[0] = sweeps; info[1] = converged; }
+}
+
+__device__ __forceinline__ uint64_t splitmix(uint64_t row, uint64_t col, uint64_t seed) {
+    uint64_t z = (row * 0x9E3779B97F4A7C15ULL) ^ (col * 0xBF58476D1CE4E5B9ULL) ^ seed;
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void hash_fill_kernel(double* W, long ld, long rows_valid, long row0, int cols, uint64_t seed) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (i >= ld) return;
+    double v = 0.0;
+    if (i < rows_valid)
+        v = (double)(splitmix((uint64_t)(row0 + i), (uint64_t)c, seed) >> 11) * 0x1.0p-52 - 1.0;
+    W[(long)c * ld + i] = v;
+}
+
+__global__ void svqb_prep_kernel(const double* G, int ldg, int b, double* Gs, double* dscale) {
+    __shared__ double d[64];
+    const int tid = threadIdx.x;
+    if (tid < b) {
+        const double gii = G[tid + (long)tid * ldg];
+        d[tid] = sqrt(fmax(gii, 1e-300));
+        dscale[tid] = d[tid];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < b * b; idx += blockDim.x) {
+        const int i = idx % b, j = idx / b;
+        // symmetrise: the two triangles come from different reduction orders
+        const double gij = 0.5 * (G[i + (long)j * ldg] + G[j + (long)i * ldg]);
+        Gs[i + j * b] = gij / (d[i] * d[j]);
+    }
+}
+
+// M = D^-1 U L^-1/2 (W_orth = W M),  Cfac = L^1/2 U' D (W = W_orth Cfac)
+__global__ void svqb_factors_kernel(const double* U, int ldu, const double* lam, const double* dscale,
+                                    int b, double tol, double* M, double* Cfac, int* ndef) {
+    __shared__ double l[64];
+    __shared__ int cnt;
+    const int tid = threadIdx.x;
+    if (tid == 0) cnt = 0;
+    __syncthreads();
+    if (tid < b) {
+        const double lmax = fmax(lam[0], 1e-300);
+        double v = lam[tid];
+        if (v < tol * lmax) { v = tol * lmax; atomicAdd(&cnt, 1); }
+        l[tid] = v;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < b * b; idx += blockDim.x) {
+        const int i = idx % b, j = idx / b;
+        M[i + j * b] = U[i + (long)j * ldu] / (sqrt(l[j]) * dscale[i]);
+        Cfac[i + j * b] = sqrt(l[i]) * U[j + (long)i * ldu] * dscale[j];
+    }
+    if (tid == 0 && ndef) *ndef = cnt;
+}
+
+__global__ void small_matmul_kernel(const double* A, const double* B, int b, double* C) {
+    for (int idx = threadIdx.x; idx < b * b; idx += blockDim.x) {
+        const int i = idx % b, j = idx / b;
+        double s = 0.0;
+        for (int k = 0; k < b; ++k) s += A[i + k * b] * B[k + j * b];
+        C[idx] = s;
+    }
+}
+
+__global__ void T_update_kernel(double* T, int ldt, const double* H, int ldh, int m0, int b) {
+    const int mq = m0 + b;
+    for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < mq * b; idx += blockDim.x * gridDim.x) {
+        const int i = idx % mq, j = idx / mq;
+        double v = H[i + (long)j * ldh];
+        if (i >= m0) v = 0.5 * (v + H[(m0 + j) + (long)(i - m0) * ldh]);   // symmetrise the diagonal block
+        T[i + (long)(m0 + j) * ldt] = v;
+        if (i < m0) T[(m0 + j) + (long)i * ldt] = v;
+    }
+}
+
+__global__ void ritz_residual_kernel(const double* C, int b, const double* S, int lds, int m, int k,
+                                     double* res) {
+    const int i = blockIdx.x;                    // Ritz pair
+    __shared__ double red[33];
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < b; r += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < b; ++c) s += C[r + c * b] * S[(m - b + c) + (long)i * lds];
+        acc += s * s;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0 && i < k) res[i] = sqrt(acc);
+}
+
+__global__ void T_restart_kernel(double* T, int ldt, int tsize, const double* theta, int r) {
+    for (long idx = threadIdx.x + (long)blockIdx.x * blockDim.x; idx < (long)tsize * tsize;
+         idx += (long)blockDim.x * gridDim.x) {
+        const int i = (int)(idx % tsize), j = (int)(idx / tsize);
+        T[i + (long)j * ldt] = (i == j && i < r) ? theta[i] : 0.0;
+    }
+}
+
+__global__ void bias_kernel(const double* colmean, const double* W, long ld, long n, int k, double* bias) {
+    __shared__ double red[33];
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (long j = threadIdx.x; j < n; j += blockDim.x) s += colmean[j] * W[(long)c * ld + j];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) bias[c] = s;
+}
+
+}  // namespace
+
+size_t fx_jacobi_work_doubles(int m) { return (size_t)m * m; }
+
+int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int ldv, double* w,
+                     double* Vwork, int* info) {
+    if (m < 1 || m > 1024) {
+        fx_set_error("jacobi: order %d out of range", m);
+        return FX_ERR_CUDA;
+    }
+    const int use_smem = (m <= J_SMEM_MAX_M) ? 1 : 0;
+    const size_t smem = use_smem ? (size_t)m * (m | 1) * 8 : 0;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        FX_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    jacobi_kernel<<<1, JT, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, use_smem, 40);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_hash_fill(fx_ctx* ctx, double* W, int64_t ld, int64_t rows_valid, int64_t row0,
+                        int cols, uint64_t seed) {
+    if (ld <= 0) return 0;
+    dim3 grid((unsigned)ceil_div(ld, 256), (unsigned)cols);
+    hash_fill_kernel<<<grid, 256, 0, ctx->stream>>>(W, ld, rows_valid, row0, cols, seed);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_svqb_prep(fx_ctx* ctx, const double* G, int ldg, int b, double* Gs, double* dscale) {
+    svqb_prep_kernel<<<1, 256, 0, ctx->stream>>>(G, ldg, b, Gs, dscale);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_svqb_factors(fx_ctx* ctx, const double* U, int ldu, const double* lam,
+                           const double* dscale, int b, double tol, double* M, double* Cfac,
+                           int* ndef) {
+    svqb_factors_kernel<<<1, 256, 0, ctx->stream>>>(U, ldu, lam, dscale, b, tol, M, Cfac, ndef);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_small_matmul(fx_ctx* ctx, const double* A, const double* B, int b, double* C) {
+    small_matmul_kernel<<<1, 256, 0, ctx->stream>>>(A, B, b, C);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_T_update(fx_ctx* ctx, double* T, int ldt, const double* H, int ldh, int m0, int b) {
+    T_update_kernel<<<8, 256, 0, ctx->stream>>>(T, ldt, H, ldh, m0, b);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_ritz_residuals(fx_ctx* ctx, const double* C, int b, const double* S, int lds,
+                             int m, int k, double* res) {
+    ritz_residual_kernel<<<k, 64, 0, ctx->stream>>>(C, b, S, lds, m, k, res);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_T_restart(fx_ctx* ctx, double* T, int ldt, int tsize, const double* theta, int r) {
+    T_restart_kernel<<<16, 256, 0, ctx->stream>>>(T, ldt, tsize, theta, r);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_bias(fx_ctx* ctx, const double* colmean, const double* W, int64_t ld, int64_t n,
+                   int k, double* bias) {
+    if (k <= 0) return 0;
+    bias_kernel<<<k, 256, 0, ctx->stream>>>(colmean, W, ld, n, k, bias);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+namespace {
+__global__ void vec_axpy_kernel(long n, double a, const double* x, double* y) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
+}
+__global__ void copy2d_kernel(const double* src, long lds, double* dst, long ldd, int rows, int cols) {
+    for (long idx = threadIdx.x + (long)blockIdx.x * blockDim.x; idx < (long)rows * cols;
+         idx += (long)blockDim.x * gridDim.x) {
+        const int i = (int)(idx % rows), j = (int)(idx / rows);
+        dst[i + j * ldd] = src[i + j * lds];
+    }
+}
+}  // namespace
+
+int fx_launch_vec_axpy(fx_ctx* ctx, int64_t n, double a, const double* x, double* y) {
+    if (n <= 0) return 0;
+    vec_axpy_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, a, x, y);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_copy2d(fx_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd, int rows,
+                     int cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    copy2d_kernel<<<32, 256, 0, ctx->stream>>>(src, lds, dst, ldd, rows, cols);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+namespace {
+__global__ void fill_kernel(double* p, long n, double v) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+}  // namespace
+int fx_launch_fill(fx_ctx* ctx, double* p, int64_t n, double v) {
+    if (n <= 0) return 0;
+    fill_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(p, n, v);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,294 @@
+// solver.cu -- top-k symmetric eigensolve on the device: thick-restart block Krylov
+// (Krylov-Schur form) whose only heavy operation is Y = K V (symm.cu), with full CGS2
+// re-orthogonalisation on DMMA tall-skinny kernels (tsgemm.cu), SVQB block orthonormalisation
+// and Rayleigh-Ritz by a device Jacobi solver (smalldense.cu).
+//
+// Replaces components_eig! -> syevd! -> ccall dsyevd_ (/root/reference/src/common.jl:161-165,
+// :107-143, :128-131), which computes ALL n eigenpairs in O(n^3); the caller of kpca
+// (kpca.jl:55) only ever uses the leading ones.  Output order is descending like
+// common.jl:164.  tests/proto_krylov.py is the step-for-step NumPy model of this file.
+//
+// Multi-GPU: K, Q, W are row-sharded; per step one all-gather of the n x b block and a few
+// all-reduces of (m+b) x b / b x b matrices; the small dense work runs redundantly on every
+// rank from identical all-reduced inputs, so all ranks take identical decisions.
+#include "fx_kernels.cuh"
+
+void fx_resolve_opts(const fx_solver_opts* in, int k, fx_solver_opts* out) {
+    fx_solver_opts o;
+    memset(&o, 0, sizeof(o));
+    if (in) o = *in;
+    int kb = (int)round_up(k, 8);
+    if (o.block <= 0) o.block = kb;
+    if (o.block < kb) o.block = kb;
+    o.block = (int)round_up(o.block, 8);
+    if (o.block > 64) o.block = 64;
+    if (o.max_blocks <= 1) o.max_blocks = 5;
+    if (o.max_steps <= 0) o.max_steps = 300;
+    if (!(o.tol > 0.0)) o.tol = 1e-12;
+    if (o.seed == 0) o.seed = 0x5eedULL;
+    if (o.cg_max_iters <= 0) o.cg_max_iters = 2000;
+    if (!(o.cg_tol > 0.0)) o.cg_tol = 1e-10;
+    *out = o;
+}
+
+namespace {
+struct Work {
+    int b, mcap, mt;
+    double *Q, *Wa, *Wb, *Vg, *Ypart, *T, *Tw, *S, *Jw, *theta, *H, *H2, *G, *Gs, *U, *Uw, *lamb,
+        *dscale, *M1, *C1, *M2, *C2, *C, *res, *tnscr;
+    int* info;
+    size_t tnscr_doubles;
+    int splits;
+};
+
+size_t carve(fx_ctx* ctx, int64_t ld, int64_t n_ld, int k, const fx_solver_opts& o, Work* w, bool commit) {
+    const int b = o.block, mcap = o.max_blocks * b, mt = mcap + b;
+    size_t total = 0;
+    auto take = [&](size_t doubles) -> double* {
+        const size_t bytes = fx_align256(doubles * sizeof(double));
+        total += bytes;
+        return commit ? (double*)fx_arena_alloc(ctx, bytes) : nullptr;
+    };
+    const int splits = fx_symm_splits(ctx, ld, n_ld);
+    size_t tn = 0;
+    for (int ma = 8; ma <= mt; ma += 8) {           // chunk count depends on ma: take the max
+        const size_t t1 = fx_ts_tn_scratch(ctx, ma, b, ld);
+        if (t1 > tn) tn = t1;
+    }
+    double* Q = take((size_t)mt * ld);
+    double* Wa = take((size_t)b * ld);
+    double* Wb = take((size_t)b * ld);
+    double* Vg = ctx->world > 1 ? take((size_t)ctx->world * b * ld) : nullptr;
+    double* Yp = splits > 1 ? take((size_t)splits * b * ld) : nullptr;
+    double* T = take((size_t)mt * mt);
+    double* Tw = take((size_t)mt * mt);
+    double* S = take((size_t)mt * mt);
+    double* Jw = take((size_t)mt * mt);
+    double* theta = take(mt);
+    double* H = take((size_t)mt * b);
+    double* H2 = take((size_t)mt * b);
+    double* G = take(64 * 64); double* Gs = take(64 * 64); double* U = take(64 * 64);
+    double* Uw = take(64 * 64); double* lamb = take(64); double* dscale = take(64);
+    double* M1 = take(64 * 64); double* C1 = take(64 * 64); double* M2 = take(64 * 64);
+    double* C2 = take(64 * 64); double* C = take(64 * 64);
+    double* res = take(64 + 8);
+    double* tnscr = take(tn);
+    int* info = (int*)take(8);
+    if (w) {
+        w->b = b; w->mcap = mcap; w->mt = mt; w->Q = Q; w->Wa = Wa; w->Wb = Wb; w->Vg = Vg;
+        w->Ypart = Yp; w->T = T; w->Tw = Tw; w->S = S; w->Jw = Jw; w->theta = theta; w->H = H;
+        w->H2 = H2; w->G = G; w->Gs = Gs; w->U = U; w->Uw = Uw; w->lamb = lamb; w->dscale = dscale;
+        w->M1 = M1; w->C1 = C1; w->M2 = M2; w->C2 = C2; w->C = C; w->res = res; w->tnscr = tnscr;
+        w->tnscr_doubles = tn; w->info = info; w->splits = splits;
+    }
+    return total;
+}
+}  // namespace
+
+size_t fx_eig_workspace_bytes(fx_ctx* ctx, int64_t ld, int64_t n_ld, int k, const fx_solver_opts& o) {
+    return carve(ctx, ld, n_ld, k, o, nullptr, false) + 4096;
+}
+
+namespace {
+
+// SVQB pass: dst[:, :b] = src[:, :b] * M with M = D^-1 U L^-1/2 from G = src'src; Cfac out.
+int svqb_pass(fx_ctx* ctx, const Work& w, const double* src, double* dst, int64_t ld, double* Mout,
+              double* Cout, int variant, FxTimer& tm, fx_stats* st) {
+    const int b = w.b;
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_tn(ctx, src, b, src, b, ld, ld, w.G, b, w.tnscr, w.tnscr_doubles, variant));
+    tm.end();
+    if (ctx->world > 1) {
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allreduce_sum(ctx->comm, w.G, (size_t)b * b, ctx->stream));
+        tm.end();
+    }
+    tm.begin(&st->rr_ms);
+    FX_TRY(fx_launch_svqb_prep(ctx, w.G, b, b, w.Gs, w.dscale));
+    FX_TRY(fx_launch_jacobi(ctx, w.Gs, b, b, w.U, b, w.lamb, w.Uw, w.info + 2));
+    FX_TRY(fx_launch_svqb_factors(ctx, w.U, b, w.lamb, w.dscale, b, 1e-14, Mout, Cout, w.info + 4));
+    tm.end();
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_nn(ctx, src, b, Mout, b, b, 1.0, 0.0, dst, ld, ld, variant));
+    tm.end();
+    return 0;
+}
+
+// W -= Q[:, :mq] (Q[:, :mq]' W);  H (ldh = mq) receives the coefficients when Hout != null
+int project_out(fx_ctx* ctx, const Work& w, int mq, double* W, int64_t ld, double* Hout, int variant,
+                FxTimer& tm, fx_stats* st) {
+    const int b = w.b;
+    double* H = Hout ? Hout : w.H2;
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_tn(ctx, w.Q, mq, W, b, ld, ld, H, mq, w.tnscr, w.tnscr_doubles, variant));
+    tm.end();
+    if (ctx->world > 1) {
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allreduce_sum(ctx->comm, H, (size_t)mq * b, ctx->stream));
+        tm.end();
+    }
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_nn(ctx, w.Q, mq, H, mq, b, -1.0, 1.0, W, ld, ld, variant));
+    tm.end();
+    return 0;
+}
+
+}  // namespace
+
+int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
+    const fx_solver_opts& o = a.opts;
+    const int variant = o.variant;
+    const int64_t ld = a.ld;
+    const int k = a.k, kp = (int)round_up(k, 8);
+    Work w;
+    carve(ctx, ld, a.n_ld, k, o, &w, true);
+    const int b = w.b, mt = w.mt;
+    cudaStream_t s = ctx->stream;
+    st->block = b;
+
+    FX_CUDA(cudaMemsetAsync(w.Q, 0, (size_t)mt * ld * 8, s));
+    FX_CUDA(cudaMemsetAsync(w.T, 0, (size_t)mt * mt * 8, s));
+
+    // start block: deterministic hash noise (independent of the number of ranks), SVQB twice
+    FX_TRY(fx_launch_hash_fill(ctx, w.Wa, ld, a.rows_valid, a.row0, b, o.seed));
+    FX_TRY(svqb_pass(ctx, w, w.Wa, w.Wb, ld, w.M1, w.C1, variant, tm, st));
+    FX_TRY(svqb_pass(ctx, w, w.Wb, w.Q, ld, w.M2, w.C2, variant, tm, st));
+
+    int m = 0, steps = 0, restarts = 0;
+    bool converged = false;
+    double maxres = 0.0;
+    double* pinned = ctx->pinned;
+
+    while (true) {
+        double* Qn = w.Q + (size_t)m * ld;
+        const int mq = m + b;
+        // 1. gather the block, 2. W = K Qn
+        const double* Vsrc = Qn;
+        if (ctx->world > 1) {
+            tm.begin(&st->comm_ms);
+            FX_TRY(fxcomm_allgather(ctx->comm, Qn, w.Vg, (size_t)b * ld, s));
+            tm.end();
+            Vsrc = w.Vg;
+        }
+        SymmArgs sa;
+        sa.K = a.K; sa.ldk = a.ldk; sa.rows_pad = ld; sa.V = Vsrc; sa.ldr = ld;
+        sa.v_rank_stride = (int64_t)b * ld; sa.bcols = b; sa.Y = w.Wa; sa.Ypart = w.Ypart;
+        sa.splits = w.splits;
+        tm.begin(&st->symm_ms);
+        FX_TRY(fx_launch_symm(ctx, sa, variant));
+        tm.end();
+        st->symm_launches++;
+        steps++;
+        // 3-5. CGS2 against [Q Qn]; H accumulates both passes
+        FX_TRY(project_out(ctx, w, mq, w.Wa, ld, w.H, variant, tm, st));
+        FX_TRY(project_out(ctx, w, mq, w.Wa, ld, nullptr, variant, tm, st));
+        FX_TRY(fx_launch_vec_axpy(ctx, (int64_t)mq * b, 1.0, w.H2, w.H));
+        // 6. projected matrix
+        FX_TRY(fx_launch_T_update(ctx, w.T, mt, w.H, mq, m, b));
+        // 7. SVQB, re-projection of the normalised block, SVQB again -> next block in place
+        FX_TRY(svqb_pass(ctx, w, w.Wa, w.Wb, ld, w.M1, w.C1, variant, tm, st));
+        FX_TRY(project_out(ctx, w, mq, w.Wb, ld, nullptr, variant, tm, st));
+        FX_TRY(svqb_pass(ctx, w, w.Wb, w.Q + (size_t)mq * ld, ld, w.M2, w.C2, variant, tm, st));
+        FX_TRY(fx_launch_small_matmul(ctx, w.C2, w.C1, b, w.C));
+        m = mq;
+        // 8. Rayleigh-Ritz
+        tm.begin(&st->rr_ms);
+        FX_TRY(fx_launch_copy2d(ctx, w.T, mt, w.Tw, mt, m, m));
+        FX_TRY(fx_launch_jacobi(ctx, w.Tw, mt, m, w.S, mt, w.theta, w.Jw, w.info));
+        FX_TRY(fx_launch_ritz_residuals(ctx, w.C, b, w.S, mt, m, k, w.res));
+        tm.end();
+        FX_CUDA(cudaMemcpyAsync(pinned, w.res, k * sizeof(double), cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaMemcpyAsync(pinned + 64, w.theta, sizeof(double), cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaMemcpyAsync(pinned + 72, w.info, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaStreamSynchronize(s));
+        const double scale = fabs(pinned[64]) > 1e-300 ? fabs(pinned[64]) : 1e-300;
+        maxres = 0.0;
+        bool finite = true;
+        for (int i = 0; i < k; ++i) {
+            if (!(pinned[i] == pinned[i])) finite = false;
+            if (pinned[i] > maxres) maxres = pinned[i];
+        }
+        maxres /= scale;
+        if (!finite) {
+            fx_set_error("eigensolver: non-finite Ritz residual at step %d", steps);
+            return FX_ERR_NOT_CONVERGED;
+        }
+        converged = maxres <= o.tol;
+        if (converged || steps >= o.max_steps) break;
+        if (m + b > w.mcap) {
+            // thick restart: keep the b leading Ritz vectors, T = diag(theta)
+            tm.begin(&st->ortho_ms);
+            FX_TRY(fx_launch_ts_nn(ctx, w.Q, m, w.S, mt, b, 1.0, 0.0, w.Wb, ld, ld, variant));
+            tm.end();
+            FX_CUDA(cudaMemcpyAsync(w.Q + (size_t)b * ld, w.Q + (size_t)m * ld, (size_t)b * ld * 8,
+                                    cudaMemcpyDeviceToDevice, s));
+            FX_CUDA(cudaMemcpyAsync(w.Q, w.Wb, (size_t)b * ld * 8, cudaMemcpyDeviceToDevice, s));
+            FX_TRY(fx_launch_T_restart(ctx, w.T, mt, mt, w.theta, b));
+            m = b;
+            restarts++;
+        }
+    }
+    st->steps = steps;
+    st->restarts = restarts;
+    st->converged = converged ? 1 : 0;
+    st->max_residual = maxres;
+
+    // Ritz vectors: V_loc = Q[:, :m] S[:, :kp], then gather all rows
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_nn(ctx, w.Q, m, w.S, mt, kp, 1.0, 0.0, w.Wa, ld, ld, variant));
+    tm.end();
+    if (ctx->world > 1) {
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allgather(ctx->comm, w.Wa, w.Vg, (size_t)kp * ld, s));
+        tm.end();
+        for (int g = 0; g < ctx->world; ++g)
+            FX_CUDA(cudaMemcpy2DAsync(a.Vout + (size_t)g * ld, a.n_ld * 8, w.Vg + (size_t)g * kp * ld,
+                                      ld * 8, ld * 8, kp, cudaMemcpyDeviceToDevice, s));
+    } else {
+        FX_CUDA(cudaMemcpyAsync(a.Vout, w.Wa, (size_t)kp * ld * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    FX_CUDA(cudaMemcpyAsync(a.theta, w.theta, kp * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (!converged) {
+        fx_set_error("eigensolver: not converged after %d K*V passes (max relative residual %.3e, tol %.1e)",
+                     steps, maxres, o.tol);
+        return FX_ERR_NOT_CONVERGED;
+    }
+    return 0;
+}
+
+// Small-n path: full Jacobi eigendecomposition of the (gathered) matrix, all on the device.
+int fx_eig_dense(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
+    const int64_t n = a.n, ld = a.ld, n_ld = a.n_ld;
+    const int k = a.k, kp = (int)round_up(k, 8);
+    cudaStream_t s = ctx->stream;
+    double* Kfull = (double*)a.K;
+    if (ctx->world > 1) {
+        Kfull = (double*)fx_arena_alloc(ctx, (size_t)n_ld * n_ld * 8);
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allgather(ctx->comm, a.K, Kfull, (size_t)ld * n_ld, s));
+        tm.end();
+    }
+    double* Vw = (double*)fx_arena_alloc(ctx, (size_t)n * n * 8);
+    double* S = (double*)fx_arena_alloc(ctx, (size_t)n * n * 8);
+    double* th = (double*)fx_arena_alloc(ctx, (size_t)(n + 8) * 8);
+    int* info = (int*)fx_arena_alloc(ctx, 64);
+    tm.begin(&st->rr_ms);
+    FX_TRY(fx_launch_jacobi(ctx, Kfull, (int)a.ldk, (int)n, S, (int)n, th, Vw, info));
+    tm.end();
+    FX_CUDA(cudaMemsetAsync(a.Vout, 0, (size_t)kp * n_ld * 8, s));
+    FX_CUDA(cudaMemcpy2DAsync(a.Vout, n_ld * 8, S, n * 8, n * 8, k, cudaMemcpyDeviceToDevice, s));
+    FX_CUDA(cudaMemsetAsync(a.theta, 0, kp * 8, s));
+    FX_CUDA(cudaMemcpyAsync(a.theta, th, k * 8, cudaMemcpyDeviceToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(ctx->pinned + 72, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    const int* hi = reinterpret_cast<const int*>(ctx->pinned + 72);
+    st->dense_path = 1;
+    st->steps = hi[0];
+    st->converged = hi[1];
+    st->block = 0;
+    if (!hi[1]) {
+        fx_set_error("dense Jacobi eigensolver did not converge in %d sweeps", hi[0]);
+        return FX_ERR_NOT_CONVERGED;
+    }
+    return 0;
+}

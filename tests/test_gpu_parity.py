@@ -1,0 +1,265 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, against the committed golden vectors, and -- at larger sizes -- through
+size-independent properties.  Tolerances (BASELINE.json north_star): eigenvalues 1e-10
+relative, subspace angle below 1e-8; kernel matrices 1e-13 absolute / relative."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import fxb200
+from fxb200.synth import mix
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+KERNELS = [
+    ("gaussian", fxb200.GaussianKernel(0.05), O.GaussianKernel(0.05)),
+    ("poly3", fxb200.PolynomialKernel(0.05, 1.0, 3.0), O.PolynomialKernel(0.05, 1.0, 3.0)),
+    ("poly2.5", fxb200.PolynomialKernel(0.01, 2.0, 2.5), O.PolynomialKernel(0.01, 2.0, 2.5)),
+    ("linear", fxb200.PolynomialKernel(1.0, 0.0, 1.0), O.PolynomialKernel(1.0, 0.0, 1.0)),
+    ("sigmoid", fxb200.SigmoidKernel(0.02, 0.3), O.SigmoidKernel(0.02, 0.3)),
+]
+
+
+def sin_angle(A, B):
+    Qa, _ = np.linalg.qr(A)
+    Qb, _ = np.linalg.qr(B)
+    return np.linalg.norm(Qb - Qa @ (Qa.T @ Qb), 2)
+
+
+def relclose(a, b, tol):
+    scale = max(np.abs(b).max(), 1e-300)
+    err = np.abs(a - b).max() / scale
+    assert err <= tol, "rel err %.3e > %.1e" % (err, tol)
+
+
+# ------------------------------------------------------------------ Gram + kernel map epilogue
+@pytest.mark.parametrize("name,kern,okern", KERNELS, ids=[k[0] for k in KERNELS])
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,d", [(300, 10), (1000, 37), (128, 16)])
+def test_gram_symmetric(gpu_ctx, name, kern, okern, variant, n, d):
+    X, _ = mix(n, d, 4, 2.0, 31)
+    K = fxb200.kernelmatrix(kern, X, ctx=gpu_ctx, variant=variant)
+    relclose(K, O.kernelmatrix(okern, X), 1e-13)
+    if name == "gaussian":
+        assert np.all(np.diag(K) == 1.0)          # exact zero distance on the diagonal
+
+
+@pytest.mark.parametrize("name,kern,okern", KERNELS[:3], ids=[k[0] for k in KERNELS[:3]])
+def test_gram_cross(gpu_ctx, name, kern, okern):
+    X, _ = mix(777, 21, 4, 2.0, 32)
+    Z, _ = mix(130, 21, 4, 2.0, 33)
+    relclose(fxb200.kernelmatrix(kern, X, Z, ctx=gpu_ctx), O.kernelmatrix(okern, Z, X), 1e-13)
+
+
+# ------------------------------------------------------------------ centring
+@pytest.mark.parametrize("n", [64, 301, 1000])
+def test_center(gpu_ctx, n):
+    X, _ = mix(n, 9, 3, 2.0, 34)
+    K = O.kernelmatrix(O.GaussianKernel(0.1), X)
+    Kc, cm, gm = fxb200.centerkernelmatrix(K, ctx=gpu_ctx)
+    Ko, r, mu = O.centerkernelmatrix(K)
+    relclose(Kc, Ko, 1e-14)
+    relclose(cm, r, 1e-14)
+    assert abs(gm - mu) <= 1e-14 * abs(mu)
+    assert np.abs(Kc.sum(0)).max() < 1e-10       # double centring: zero column sums
+
+
+# ------------------------------------------------------------------ K*V (SYMM)
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,b", [(256, 8), (1000, 16), (1300, 24), (700, 40), (513, 64), (200, 5)])
+def test_symm(gpu_ctx, variant, n, b):
+    rng = np.random.default_rng(35)
+    A = rng.standard_normal((n, n)); K = A + A.T
+    V = rng.standard_normal((n, b))
+    relclose(fxb200.symm(K, V, ctx=gpu_ctx, variant=variant), K @ V, 1e-13)
+
+
+# ------------------------------------------------------------------ small dense eigensolver
+@pytest.mark.parametrize("m", [1, 2, 5, 16, 33, 96, 160, 161, 300])
+def test_syevd_small(gpu_ctx, m):
+    rng = np.random.default_rng(36)
+    A = rng.standard_normal((m, m)); A = A + A.T
+    w, V, sweeps = fxb200.syevd_small(A, ctx=gpu_ctx)
+    wo = np.linalg.eigvalsh(A)[::-1]
+    scale = max(np.abs(wo).max(), 1e-300)
+    assert np.abs(w - wo).max() <= 1e-13 * scale
+    assert np.abs(V.T @ V - np.eye(m)).max() < 1e-12
+    assert np.abs(A @ V - V * w[None, :]).max() <= 1e-12 * scale
+    assert sweeps <= 20
+
+
+# ------------------------------------------------------------------ KPCA fit
+def check_fit(V, L, Vo, Lo, k):
+    np.testing.assert_allclose(L, Lo[:k], rtol=1e-10)
+    assert sin_angle(V, Vo[:, :k]) < 1e-8
+    np.testing.assert_allclose(np.linalg.norm(V, axis=0), 1.0, atol=1e-12)
+
+
+def test_reference_identity_kpca_vs_pca(gpu_ctx):
+    """test_kpca.jl:44-56 through the CUDA path: KPCA with PolynomialKernel(1,0,1) == PCA
+    (all n eigenpairs: the small-n dense path)."""
+    n, p = 20, 5
+    X = np.random.default_rng(7).random((n, p))
+    Xc = X - X.mean(0)
+    S = Xc.T @ Xc / (n - 1)
+    for eps in (0.0, 1.0):
+        V1, D1 = fxb200.kpca(X, fxb200.PolynomialKernel(1.0, 0.0, 1.0), 0.0, eps, ctx=gpu_ctx)
+        V2, D2 = O.pca(X.copy(), 0.0, eps)
+        a = (V1.T @ Xc @ Xc.T @ V1 / (n - 1))[:p, :p]
+        b = V2.T @ S @ V2
+        assert np.abs(a - b).max() < 1e-12
+        np.testing.assert_allclose(np.abs(D1)[:p], np.abs(D2), rtol=1e-12)
+        assert V1.shape == (n, n) and np.all(np.diff(D1) <= 1e-15)
+
+
+@pytest.mark.parametrize("name,kern,okern", [KERNELS[0], KERNELS[1], KERNELS[4]],
+                         ids=["gaussian", "poly3", "sigmoid"])
+def test_kpca_fit_matches_oracle(gpu_ctx, name, kern, okern):
+    X, _ = mix(1500, 20, 5, 3.0, 41)
+    k = 4
+    V, L, st = fxb200.kpca(X, kern, k=k, ctx=gpu_ctx, return_stats=True)
+    Vo, Lo = O.kpca(X, okern)
+    check_fit(V, L, Vo, Lo, k)
+    assert st["converged"] == 1 and st["dense_path"] == 0 and st["kernel_launches"] > 10
+
+
+def test_kpca_config_C1(gpu_ctx):
+    """BASELINE.json configs[0]: RBF n=1000 d=10 k=2, fit + transform of 200 fresh points."""
+    cfg = fxb200.synth.CONFIGS["C1"]
+    X, _ = mix(cfg["n"], cfg["d"], cfg["c"], cfg["sep"], cfg["seed"])
+    Z, _ = mix(200, cfg["d"], cfg["c"], cfg["sep"], 1002)
+    kern, okern = fxb200.GaussianKernel(0.1), O.GaussianKernel(0.1)
+    V, L, model = fxb200.kpca(X, kern, k=2, ctx=gpu_ctx, return_model=True)
+    Vo, Lo = O.kpca(X, okern)
+    check_fit(V, L, Vo, Lo, 2)
+    T = model.transform(Z)
+    relclose(T, O.transform_kpca(X, okern, V, Z), 1e-10)
+    relclose(model.transform(Z, _naive=True), T, 1e-11)
+    relclose(fxb200.transform_kpca(X, kern, V, Z, ctx=gpu_ctx), T, 1e-10)   # stateless signature
+    relclose(model.transform(X), V * (L * (len(X) - 1))[None, :], 1e-9)     # in-sample identity
+    model.free()
+
+
+def test_kpca_naive_variant_agrees(gpu_ctx):
+    X, _ = mix(900, 12, 4, 3.0, 42)
+    kern = fxb200.GaussianKernel(1 / 12)
+    V0, L0 = fxb200.kpca(X, kern, k=3, ctx=gpu_ctx)
+    V1, L1 = fxb200.kpca(X, kern, k=3, ctx=gpu_ctx, opts=fxb200.make_opts(variant=1))
+    np.testing.assert_allclose(L0, L1, rtol=1e-12)
+    assert sin_angle(V0, V1) < 1e-9
+
+
+def test_kpca_alpha_eps_center(gpu_ctx):
+    X, _ = mix(700, 8, 4, 3.0, 43)
+    kern, okern = fxb200.GaussianKernel(0.125), O.GaussianKernel(0.125)
+    for alpha, eps in [(0.3, 0.0), (0.0, 0.5), (0.5, 1.0)]:
+        V, L = fxb200.kpca(X, kern, alpha, eps, k=3, ctx=gpu_ctx)
+        Vo, Lo = O.kpca(X, okern, alpha, eps)
+        check_fit(V, L, Vo, Lo, 3)
+    V, L = fxb200.kpca(X, kern, k=3, center=False, ctx=gpu_ctx)
+    Vo, Lo = O.kpca(X, okern, center=False)
+    check_fit(V, L, Vo, Lo, 3)
+    # alpha = 1: K' = beta I, every eigenvalue equals tr(K~)/n/(n-1) (degenerate basis)
+    _V, L = fxb200.kpca(X, kern, 1.0, 0.0, k=3, ctx=gpu_ctx)
+    _Vo, Lo = O.kpca(X, okern, 1.0, 0.0)
+    np.testing.assert_allclose(L, Lo[:3], rtol=1e-10)
+
+
+def test_kpca_low_rank_kernel(gpu_ctx):
+    """Linear kernel with d < block width: K~ has rank d, the Krylov block goes rank deficient."""
+    X, _ = mix(2000, 5, 3, 3.0, 44)
+    V, L = fxb200.kpca(X, fxb200.PolynomialKernel(1.0, 0.0, 1.0), k=5, ctx=gpu_ctx)
+    Vo, Lo = O.kpca(X, O.PolynomialKernel(1.0, 0.0, 1.0))
+    check_fit(V, L, Vo, Lo, 5)
+    _V2, D2 = O.pca(X)
+    np.testing.assert_allclose(L, D2, rtol=1e-10)      # == PCA eigenvalues (test_kpca.jl:55)
+
+
+def test_kpca_slow_decay_restarts(gpu_ctx):
+    rng = np.random.default_rng(45)
+    X = rng.standard_normal((1400, 16))
+    kern, okern = fxb200.GaussianKernel(1 / 16), O.GaussianKernel(1 / 16)
+    V, L, st = fxb200.kpca(X, kern, k=6, ctx=gpu_ctx, return_stats=True,
+                           opts=fxb200.make_opts(max_blocks=3))
+    Vo, Lo = O.kpca(X, okern)
+    np.testing.assert_allclose(L, Lo[:6], rtol=1e-10)
+    assert st["restarts"] >= 1 and st["converged"] == 1
+
+
+def test_kpca_medium(gpu_ctx):
+    X, _ = mix(4096, 128, 9, 3.0, 46)
+    kern, okern = fxb200.GaussianKernel(1 / 128), O.GaussianKernel(1 / 128)
+    V, L, model = fxb200.kpca(X, kern, k=8, ctx=gpu_ctx, return_model=True)
+    Vo, Lo = O.kpca(X, okern)
+    check_fit(V, L, Vo, Lo, 8)
+    Z, _ = mix(1000, 128, 9, 3.0, 47)
+    relclose(model.transform(Z), O.transform_kpca(X, okern, V, Z), 1e-10)
+    model.free()
+
+
+# ------------------------------------------------------------------ golden vectors
+GOLD = sorted(glob.glob(os.path.join(HERE, "golden", "kpca_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(f) for f in GOLD])
+def test_golden(gpu_ctx, path):
+    g = np.load(path)
+    n, d, c, sep, seed, k, m, zseed = g["meta"]
+    X, _ = mix(int(n), int(d), int(c), float(sep), int(seed))
+    Z, _ = mix(int(m), int(d), int(c), float(sep), int(zseed))
+    kern = fxb200.from_spec(str(g["kernel"]), tuple(g["params"]))
+    K = fxb200.kernelmatrix(kern, X, ctx=gpu_ctx)
+    relclose(K[g["rows"]], g["K_rows"], 1e-13)
+    Kc, cm, gm = fxb200.centerkernelmatrix(K, ctx=gpu_ctx)
+    relclose(Kc[g["rows"]], g["Kc_rows"], 1e-13)
+    relclose(cm, g["colmean"], 1e-13)
+    V, L, model = fxb200.kpca(X, kern, k=int(k), ctx=gpu_ctx, return_model=True)
+    np.testing.assert_allclose(L, g["L"], rtol=1e-10)
+    assert np.abs(np.abs(V) - g["V_abs"]).max() < 1e-8
+    relclose(np.abs(model.transform(Z)), g["T_abs"], 1e-8)
+    model.free()
+
+
+# ------------------------------------------------------------------ size-independent properties
+def test_properties_large(gpu_ctx):
+    """n = 16,384 (BASELINE configs[1]): the dense oracle needs minutes here, so check the
+    eigen-relation through the library itself: transform(X) = K~ V = V diag(lambda (n-1)),
+    V'V = I, 1'V = 0, descending eigenvalues, trace bound."""
+    cfg = fxb200.synth.CONFIGS["C2"]
+    X, _ = mix(cfg["n"], cfg["d"], cfg["c"], cfg["sep"], cfg["seed"])
+    n = len(X)
+    kern = fxb200.GaussianKernel(cfg["params"][0])
+    V, L, model, st = fxb200.kpca(X, kern, k=cfg["k"], ctx=gpu_ctx, return_model=True,
+                                  return_stats=True)
+    assert st["converged"] == 1
+    assert np.abs(V.T @ V - np.eye(cfg["k"])).max() < 1e-12
+    assert np.abs(V.sum(0)).max() < 1e-9
+    assert np.all(np.diff(L) < 0) and L[-1] > 0
+    lam = L * (n - 1)
+    assert lam.sum() <= st["trace"] * (1 + 1e-12)
+    R = model.transform(X) - V * lam[None, :]
+    assert np.abs(R).max() <= 1e-9 * lam[0]
+    model.free()
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors(gpu_ctx):
+    X = np.random.default_rng(1).random((50, 3))
+    with pytest.raises(ValueError):
+        fxb200.kpca(X, fxb200.GaussianKernel(1.0), k=51, ctx=gpu_ctx)
+    with pytest.raises(ValueError):
+        fxb200.kpca(X, fxb200.GaussianKernel(1.0), 1.5, 0.0, k=2, ctx=gpu_ctx)
+    with pytest.raises(fxb200.DimensionMismatch):
+        fxb200.centerkernelmatrix(np.zeros((3, 4)), ctx=gpu_ctx)
+    with pytest.raises(fxb200.DimensionMismatch):
+        fxb200.syevd_small(np.zeros((3, 4)), ctx=gpu_ctx)
+    V, L, model = fxb200.kpca(X, fxb200.GaussianKernel(1.0), k=2, ctx=gpu_ctx, return_model=True)
+    with pytest.raises(fxb200.DimensionMismatch):
+        model.transform(np.zeros((4, 5)))
+    with pytest.raises(fxb200.DimensionMismatch):
+        fxb200.transform_kpca(X, fxb200.GaussianKernel(1.0), np.zeros((49, 2)), X, ctx=gpu_ctx)
+    model.free()
