@@ -57,9 +57,14 @@ void FxTimer::begin(double* acc) {
     sp.b = get_event();
     sp.acc = acc;
     cudaEventRecord(sp.a, ctx->stream);
+    open_.push_back((int)spans.size());
     spans.push_back(sp);
 }
-void FxTimer::end() { cudaEventRecord(spans.back().b, ctx->stream); }
+void FxTimer::end() {
+    if (open_.empty()) return;
+    cudaEventRecord(spans[open_.back()].b, ctx->stream);
+    open_.pop_back();
+}
 int FxTimer::resolve() {
     for (auto& sp : spans) {
         float ms = 0.f;
@@ -67,6 +72,7 @@ int FxTimer::resolve() {
         else cudaGetLastError();
     }
     spans.clear();
+    open_.clear();
     ctx->ev_used = 0;
     return 0;
 }

@@ -23,6 +23,23 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
     if (s == 123.456) out[0] = s;
 }
 
+// sweep variant: ILP independent accumulators per warp, any block size
+template <int ILP>
+__global__ void dmma_sweep_kernel(double* out, int iters) {
+    double c[ILP][2];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) dmma(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
     double c[16];
 #pragma unroll
@@ -95,6 +112,27 @@ extern "C" int fx_bench_kernel(fx_ctx* ctx, int which, int64_t n, int64_t d, int
         return time_loop(ctx, reps, ms_out, [&]() -> int {
             if (which == 4) dmma_peak_kernel<<<grid, 256, 0, s>>>(out, iters);
             else dfma_peak_kernel<<<grid, 256, 0, s>>>(out, iters);
+            ctx->launches++;
+            FX_LAUNCH_CHECK();
+            return 0;
+        });
+    }
+    if (which == 7) {
+        // DMMA issue sweep: n = CTAs per SM, b = warps per CTA, d = independent accumulators
+        FX_TRY(fx_arena_reserve(ctx, 4096));
+        fx_arena_reset(ctx);
+        double* out = (double*)fx_arena_alloc(ctx, 256);
+        const int grid = ctx->sm_count * (int)n, threads = 32 * b, ilp = (int)d;
+        const int iters = (int)m;
+        return time_loop(ctx, reps, ms_out, [&]() -> int {
+            switch (ilp) {
+                case 1: dmma_sweep_kernel<1><<<grid, threads, 0, s>>>(out, iters); break;
+                case 2: dmma_sweep_kernel<2><<<grid, threads, 0, s>>>(out, iters); break;
+                case 4: dmma_sweep_kernel<4><<<grid, threads, 0, s>>>(out, iters); break;
+                case 8: dmma_sweep_kernel<8><<<grid, threads, 0, s>>>(out, iters); break;
+                case 16: dmma_sweep_kernel<16><<<grid, threads, 0, s>>>(out, iters); break;
+                default: dmma_sweep_kernel<32><<<grid, threads, 0, s>>>(out, iters); break;
+            }
             ctx->launches++;
             FX_LAUNCH_CHECK();
             return 0;

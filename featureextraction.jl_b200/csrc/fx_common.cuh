@@ -80,8 +80,9 @@ struct FxTimer {
     explicit FxTimer(fx_ctx* c) : ctx(c) {}
     ~FxTimer() { ctx->ev_used = 0; }
     cudaEvent_t get_event();
+    std::vector<int> open_;       // stack of open spans (begin/end nest)
     void begin(double* acc);      // records start on ctx->stream
-    void end();                   // records end for the last begun span
+    void end();                   // records end for the innermost open span
     int  resolve();               // after stream sync: adds elapsed ms to every accumulator
 };
 
