@@ -170,28 +170,73 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Branch-free exp(x) for x <= 0 (the Gaussian kernel's argument): Cody-Waite reduction by
+// ln2 (hi/lo), degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), scaling by two
+// exact powers of two so results below the normal range flush smoothly to 0.  No slow path, so
+// unrolled callers interleave many independent chains on the FP64 pipe.
+__device__ __forceinline__ double fx_exp_nonpos(double x) {
+    x = fmax(x, -746.0);
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);   // round-to-nearest via magic
+    const int n = __double2loint(t);
+    const double fn = t - 6755399441055744.0;
+    double r = fma(fn, -6.93147180369123816490e-01, x);
+    r = fma(fn, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                 // 1/13!
+    p = fma(p, r, 2.08767569878680990e-09);            // 1/12!
+    p = fma(p, r, 2.50521083854417188e-08);            // 1/11!
+    p = fma(p, r, 2.75573192239858907e-07);            // 1/10!
+    p = fma(p, r, 2.75573192239858907e-06);            // 1/9!
+    p = fma(p, r, 2.48015873015873016e-05);            // 1/8!
+    p = fma(p, r, 1.98412698412698413e-04);            // 1/7!
+    p = fma(p, r, 1.38888888888888889e-03);            // 1/6!
+    p = fma(p, r, 8.33333333333333333e-03);            // 1/5!
+    p = fma(p, r, 4.16666666666666667e-02);            // 1/4!
+    p = fma(p, r, 1.66666666666666667e-01);            // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int n1 = n >> 1, n2 = n - n1;                // n in [-1077, 0]: both exponents normal
+    const double s1 = __hiloint2double((n1 + 1023) << 20, 0);
+    const double s2 = __hiloint2double((n2 + 1023) << 20, 0);
+    return (p * s1) * s2;
+}
+
 // kernel map of a dot product (and squared norms for the Gaussian), see include/fxb200.h
 struct KernelMap {
     int id;
     double p0, p1, p2;
     int ipow;      // integer exponent when p2 is a small positive integer, else 0
 };
+// compile-time kernel selector: 0 Gaussian, 1 polynomial with integer power, 2 sigmoid,
+// 3 polynomial with a general real power
+template <int KID>
+__device__ __forceinline__ double kernel_map_t(const KernelMap& km, double dot, double ni, double nj,
+                                               bool same_point) {
+    if (KID == 0) {
+        double d2 = fmax(ni + nj - 2.0 * dot, 0.0);
+        d2 = same_point ? 0.0 : d2;
+        return fx_exp_nonpos(-km.p0 * d2);
+    } else if (KID == 1) {
+        const double base = fma(km.p0, dot, km.p1);
+        double r = base;
+        for (int e = 1; e < km.ipow; ++e) r *= base;
+        return r;
+    } else if (KID == 2) {
+        return tanh(fma(km.p0, dot, km.p1));
+    } else {
+        return pow(fma(km.p0, dot, km.p1), km.p2);
+    }
+}
+static __host__ __device__ __forceinline__ int kernel_variant(int id, int ipow) {
+    return id == FX_KERNEL_GAUSSIAN ? 0 : (id == FX_KERNEL_SIGMOID ? 2 : (ipow > 0 ? 1 : 3));
+}
 __device__ __forceinline__ double kernel_map(const KernelMap& km, double dot, double ni,
                                              double nj, bool same_point) {
-    if (km.id == FX_KERNEL_GAUSSIAN) {
-        double d2 = fmax(ni + nj - 2.0 * dot, 0.0);
-        if (same_point) d2 = 0.0;
-        return exp(-km.p0 * d2);
-    } else if (km.id == FX_KERNEL_POLYNOMIAL) {
-        double base = km.p0 * dot + km.p1;
-        if (km.ipow > 0) {
-            double r = base;
-            for (int e = 1; e < km.ipow; ++e) r *= base;
-            return r;
-        }
-        return pow(base, km.p2);
-    } else {
-        return tanh(km.p0 * dot + km.p1);
+    switch (kernel_variant(km.id, km.ipow)) {
+        case 0: return kernel_map_t<0>(km, dot, ni, nj, same_point);
+        case 1: return kernel_map_t<1>(km, dot, ni, nj, same_point);
+        case 2: return kernel_map_t<2>(km, dot, ni, nj, same_point);
+        default: return kernel_map_t<3>(km, dot, ni, nj, same_point);
     }
 }
 #endif  // __CUDACC__

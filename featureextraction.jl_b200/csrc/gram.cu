@@ -2,11 +2,14 @@
 // per-tile row sums fused into the epilogue.  Replaces MLKernels.kernelmatrix as called at
 // /root/reference/src/kpca.jl:51 (symmetric) and kpca.jl:65 (cross).
 //
-// Data path (per 128x64 output tile, 4 warps, 2 CTAs/SM):
-//   HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier--> 4-stage smem ring of 16-feature
-//   slabs --LDS.64 conflict-free (row stride = 4 mod 16 doubles)--> DMMA.8x8x4 (mma.sync f64)
-//   64x32 register tile per warp --> smem staging --> kernel map + warp-shuffle row sums
-//   --> 16-byte coalesced stores (a warp writes 512 contiguous bytes of one K row).
+// Data path (per 128x64 output tile; 4 MMA warps + 1 producer warp; 2 CTAs/SM):
+//   producer warp: HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 4-stage
+//     smem ring of 16-feature slabs (no CTA-wide barrier in the main loop)
+//   MMA warps: LDS.64 conflict-free (row stride = 4 mod 16 doubles) --> DMMA.8x8x4
+//     (mma.sync f64), 64x32 register tile per warp
+//   epilogue: kernel map applied IN REGISTERS (64 independent elements per thread, branch-free
+//     exp) --> row sums by 2-step warp shuffle --> smem staging --> 16-byte coalesced stores
+//     (a warp writes 512 contiguous bytes of one K row).
 #include "fx_kernels.cuh"
 
 namespace {
@@ -16,7 +19,7 @@ constexpr int AS = BM + 4;                      // 132: (t*AS + g) mod 16 distin
 constexpr int BS = BN + 4;                      // 68
 constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25600 B)
 constexpr int CS = 72;                          // staging row stride (conflict-free STS.128)
-constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 64;
+constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 2 * BM * 8 + 128;
 static_assert(BM * CS <= STAGES * STAGE_D, "staging tile must fit in the pipeline buffers");
 
 struct GramParams {
@@ -30,39 +33,52 @@ struct GramParams {
     KernelMap km;
 };
 
-__global__ void __launch_bounds__(128, 2) gram_dmma_kernel(const GramParams p) {
+__device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int KID>
+__global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_D * 8);
+    double* rs = smem + (size_t)STAGES * STAGE_D;                  // [2][BM] row-sum halves
+    uint64_t* full = reinterpret_cast<uint64_t*>(rs + 2 * BM);
+    uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 1, wn = warp & 1;
     const long i0 = (long)blockIdx.y * BM;
     const long j0 = (long)blockIdx.x * BN;
     const int KT = p.kt;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
         fence_mbar_init();
     }
     __syncthreads();
 
-    auto issue = [&](int kt, int s) {           // all 32 lanes of warp 0
-        double* As = smem + (size_t)s * STAGE_D;
-        double* Bs = As + BK * AS;
-        if (lane == 0) mbar_arrive_expect_tx(&full[s], BK * (BM + BN) * 8);
-        __syncwarp();
-        if (lane < BK)
-            bulk_g2s(As + lane * AS, p.A + (long)(kt * BK + lane) * p.lda + i0, BM * 8, &full[s]);
-        else
-            bulk_g2s(Bs + (lane - BK) * BS, p.B + (long)(kt * BK + lane - BK) * p.ldb + j0, BN * 8,
-                     &full[s]);
-    };
-    if (warp == 0)
-        for (int s = 0; s < STAGES && s < KT; ++s) issue(s, s);
+    if (warp >= 4) {
+        // ---------------- producer warpgroup: hands its registers to the MMA warps ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp != 4) return;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);        // passes at once on first use
+            double* As = smem + (size_t)s * STAGE_D;
+            double* Bs = As + BK * AS;
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], BK * (BM + BN) * 8);
+            __syncwarp();
+            if (lane < BK)
+                bulk_g2s(As + lane * AS, p.A + (long)(kt * BK + lane) * p.lda + i0, BM * 8, &full[s]);
+            else
+                bulk_g2s(Bs + (lane - BK) * BS, p.B + (long)(kt * BK + lane - BK) * p.ldb + j0, BN * 8,
+                         &full[s]);
+        }
+        return;
+    }
 
+    // -------------------------------- MMA warps --------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int wm = warp >> 1, wn = warp & 1;
     double acc[8][4][2];
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt)
@@ -87,12 +103,54 @@ __global__ void __launch_bounds__(128, 2) gram_dmma_kernel(const GramParams p) {
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
         }
-        __syncthreads();                         // every warp is done with stage s
-        if (warp == 0 && kt + STAGES < KT) issue(kt + STAGES, s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);                   // this warp is done with stage s
     }
 
-    // ---- epilogue: registers -> smem staging tile -> map + row sums -> coalesced stores ----
-    double* Cs = smem;                           // all bulk copies have landed and been consumed
+    // ---- epilogue: map in registers, shuffle row sums, stage through smem, coalesced stores ----
+    double nbv[4][2];
+    bool jv[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const long j = j0 + wn * 32 + nt * 8 + 2 * t;
+        jv[nt][0] = j < p.cols_valid;
+        jv[nt][1] = (j + 1) < p.cols_valid;
+        nbv[nt][0] = nbv[nt][1] = 0.0;
+        if (KID == 0) {
+            const double2 v = *reinterpret_cast<const double2*>(p.nb + j);
+            nbv[nt][0] = v.x; nbv[nt][1] = v.y;
+        }
+    }
+    double rsum[8];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+        const long i = i0 + wm * 64 + mt * 8 + g;
+        const bool iv = i < p.rows_valid;
+        const double ni = (KID == 0) ? p.na[i] : 0.0;
+        const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+        double sacc = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const long j = j0 + wn * 32 + nt * 8 + 2 * t;
+            const double v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni, nbv[nt][0], ig == j);
+            const double v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni, nbv[nt][1], ig == j + 1);
+            acc[mt][nt][0] = (iv && jv[nt][0]) ? v0 : 0.0;
+            acc[mt][nt][1] = (iv && jv[nt][1]) ? v1 : 0.0;
+            sacc += acc[mt][nt][0] + acc[mt][nt][1];
+        }
+        rsum[mt] = sacc;
+    }
+    if (p.rowpart) {
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+            double v = rsum[mt];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t == 0) rs[wn * BM + wm * 64 + mt * 8 + g] = v;
+        }
+    }
+    bar_sync_compute();                          // every MMA warp is done reading the ring
+    double* Cs = smem;
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
@@ -100,34 +158,14 @@ __global__ void __launch_bounds__(128, 2) gram_dmma_kernel(const GramParams p) {
             const int r = wm * 64 + mt * 8 + g, c = wn * 32 + nt * 8 + 2 * t;
             *reinterpret_cast<double2*>(&Cs[r * CS + c]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         }
-    __syncthreads();
-
-    const long j = j0 + 2 * lane;
-    const bool jv0 = j < p.cols_valid, jv1 = (j + 1) < p.cols_valid;
-    double nb0 = 0.0, nb1 = 0.0;
-    if (p.km.id == FX_KERNEL_GAUSSIAN) {
-        nb0 = p.nb[j];
-        nb1 = p.nb[j + 1];
-    }
-    const int jt = blockIdx.x;
-#pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-        const int r = warp * 32 + rr;
-        const long i = i0 + r;
-        const double2 dot = *reinterpret_cast<const double2*>(&Cs[r * CS + 2 * lane]);
-        double v0 = 0.0, v1 = 0.0;
-        if (i < p.rows_valid) {
-            const double ni = (p.km.id == FX_KERNEL_GAUSSIAN) ? p.na[i] : 0.0;
-            const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
-            if (jv0) v0 = kernel_map(p.km, dot.x, ni, nb0, ig == j);
-            if (jv1) v1 = kernel_map(p.km, dot.y, ni, nb1, ig == j + 1);
-        }
-        *reinterpret_cast<double2*>(&p.K[i * p.ldk + j]) = make_double2(v0, v1);
-        if (p.rowpart) {
-            const double s = warp_sum(v0 + v1);
-            if (lane == 0) p.rowpart[(long)jt * p.rows_pad + i] = s;
-        }
-    }
+    bar_sync_compute();
+    double* Kout = p.K + (i0 + warp * 32) * p.ldk + j0 + 2 * lane;
+    const double* Crow = Cs + (warp * 32) * CS + 2 * lane;
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr)
+        *reinterpret_cast<double2*>(Kout + (long)rr * p.ldk) = *reinterpret_cast<const double2*>(Crow + rr * CS);
+    if (p.rowpart && tid < BM)
+        p.rowpart[(long)blockIdx.x * p.rows_pad + i0 + tid] = rs[tid] + rs[BM + tid];
 }
 
 // ---- naive cross-check variant: one thread per output element -------------------------------
@@ -199,11 +237,19 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     if (variant == 0) {
         static bool attr_set = false;
         if (!attr_set) {
-            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             attr_set = true;
         }
         dim3 grid((unsigned)(a.ldk / BN), (unsigned)(a.rows_pad / BM));
-        gram_dmma_kernel<<<grid, 128, SMEM_BYTES, ctx->stream>>>(p);
+        switch (kernel_variant(p.km.id, p.km.ipow)) {
+            case 0: gram_dmma_kernel<0><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 1: gram_dmma_kernel<1><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 2: gram_dmma_kernel<2><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            default: gram_dmma_kernel<3><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+        }
         ctx->launches++;
     } else {
         dim3 grid((unsigned)ceil_div(a.ldk, 256), (unsigned)a.rows_pad);

@@ -3,35 +3,79 @@
 // n x b block.  This is the only heavy operation of the top-k eigensolve that replaces the
 // dense dsyevd_ call of /root/reference/src/common.jl:128-131 (via components_eig!, :161-165).
 //
-// Work unit = (128-row tile, k-split).  Per unit a 2-stage ring of {128 x 64 slab of K, 64 x b
-// slab of V} is filled by cp.async.bulk (UBLKCP) row copies completing on mbarriers; 8 warps
-// each own 16 rows x b columns of the output and feed DMMA.8x8x4 straight from LDS.128
-// fragments (row stride 66 doubles => conflict-free quarter-warps).  Thread (g,t) of a warp
-// owns k = 16*s + 4*t + e for the e-th MMA of a 16-wide step, for A and B alike, so one
-// 32-byte load serves four MMAs.  K-split partials are reduced by a second tiny kernel in a
-// fixed order (deterministic, no atomics).
+// Work unit = (128-row tile, k-split).  One producer warp drives the TMA engine with tensor
+// maps (cp.async.bulk.tensor, SASS UTMALDG): per stage ONE 3-D box {16 x 128 rows x 4} of K
+// (64 KB, L2 evict-first: streamed once) and ONE 4-D box of V (L2 evict-last: reused by every
+// row tile), 128-byte swizzle, completion on mbarrier full/empty pairs -- no CTA-wide barrier in
+// the main loop.  8 MMA warps each own 16 rows x b columns of the output and feed DMMA.8x8x4
+// straight from LDS.128 fragments: thread (g,t) owns k = 16 s + 4 t + e for the e-th MMA of a
+// 16-wide step, for A and B alike, so one 32-byte load serves four MMAs, and with the swizzle
+// chunk' = chunk ^ (row & 7) every quarter-warp hits 8 distinct 16-byte banks.
+// K-split partials are reduced by a second tiny kernel in a fixed order (deterministic).
+#include <cuda.h>
 #include "fx_kernels.cuh"
 
 namespace {
 
 constexpr int RT = 128;            // rows per tile
 constexpr int BKC = 64;            // k-chunk (columns of K per stage)
-constexpr int KS = BKC + 2;        // 66: smem row stride (doubles)
-constexpr int NSTAGE = 2;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
 
 struct SymmParams {
-    const double* K; long ldk; long rows_pad;
-    const double* V; long ldr; long v_rank_stride;
+    long rows_pad; long ldr;
     double* Yp;                    // [splits][bcols][rows_pad]
-    int nchunks, splits, bcols;
+    int nchunks, splits, bcols, nstage;
 };
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            uint64_t* bar, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)),
+        "l"(hint)
+        : "memory");
+}
+
 template <int NB>
-__global__ void __launch_bounds__(256, 1) symm_dmma_kernel(const SymmParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int STAGE_D = (RT + NB * 8) * KS;
-    double* smem = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_D * 8);
+__global__ void __launch_bounds__(288, 1)
+symm_dmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                 const SymmParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte alignment so that (address bits 7..9) == (row & 7) for the 128-byte swizzle
+    unsigned char* base = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    constexpr int K_BYTES = RT * BKC * 8;                 // 65536
+    constexpr int V_BYTES = NB * 8 * BKC * 8;             // NB * 4096
+    constexpr int STAGE_BYTES = K_BYTES + V_BYTES;        // multiple of 1024
+    const int NS = p.nstage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)NS * STAGE_BYTES);
+    uint64_t* empty = full + 4;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -42,54 +86,58 @@ __global__ void __launch_bounds__(256, 1) symm_dmma_kernel(const SymmParams p) {
     const int nc = c_end - c_begin;
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
         fence_mbar_init();
     }
     __syncthreads();
 
-    constexpr uint32_t STAGE_TX = (RT + NB * 8) * BKC * 8;
-    auto issue = [&](int ci, int s) {            // every thread: at most one row copy
-        double* Ks = smem + (size_t)s * STAGE_D;
-        const long kg = (long)(c_begin + ci) * BKC;
-        if (tid == 0) mbar_arrive_expect_tx(&full[s], STAGE_TX);
-        if (tid < RT) {
-            bulk_g2s(Ks + tid * KS, p.K + (rt * RT + tid) * p.ldk + kg, BKC * 8, &full[s]);
-        } else if (tid < RT + NB * 8) {
-            const int c = tid - RT;
-            const long rk = kg / p.ldr;
-            bulk_g2s(Ks + (RT + c) * KS, p.V + rk * p.v_rank_stride + (long)c * p.ldr + (kg - rk * p.ldr),
-                     BKC * 8, &full[s]);
+    if (warp == 8) {
+        // ------------------------------ producer warp (one elected lane) ------------------------------
+        if (lane == 0) {
+            const int slabs_per_rank = (int)(p.ldr / 16);
+            for (int ci = 0; ci < nc; ++ci) {
+                const int s = ci % NS;
+                mbar_wait(&empty[s], ((ci / NS) & 1) ^ 1);
+                unsigned char* st = base + (size_t)s * STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+                const int slab = (c_begin + ci) * (BKC / 16);             // global 16-column slab index
+                tma_load_3d(st, &tmK, 0, (int)(rt * RT), slab, &full[s], L2_EVICT_FIRST);
+                const int rk = slab / slabs_per_rank;
+                tma_load_4d(st + K_BYTES, &tmV, 0, 0, slab - rk * slabs_per_rank, rk, &full[s], L2_EVICT_LAST);
+            }
         }
-    };
-    if (nc > 0) issue(0, 0);
-    if (nc > 1) issue(1, 1);
+        return;
+    }
 
+    // -------------------------------- MMA warps --------------------------------
     double acc[2][NB][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NB; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
+    // per-thread swizzled offsets (doubles) inside a 16-column slab row: chunks 2t and 2t+1
+    const int off0 = ((2 * t) ^ g) * 2, off1 = ((2 * t + 1) ^ g) * 2;
     for (int ci = 0; ci < nc; ++ci) {
-        const int s = ci & 1;
-        mbar_wait(&full[s], (ci >> 1) & 1);
-        const double* Ks = smem + (size_t)s * STAGE_D;
-        const double* Ar = Ks + (warp * 16 + g) * KS + 4 * t;
-        const double* Br = Ks + (RT + g) * KS + 4 * t;
+        const int s = ci % NS;
+        mbar_wait(&full[s], (ci / NS) & 1);
+        const double* Ks = reinterpret_cast<const double*>(base + (size_t)s * STAGE_BYTES);
+        const double* Vs = Ks + RT * BKC;
 #pragma unroll
         for (int s16 = 0; s16 < BKC / 16; ++s16) {
             double a[2][4], b[NB][4];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                const double2 lo = *reinterpret_cast<const double2*>(Ar + mt * 8 * KS + s16 * 16);
-                const double2 hi = *reinterpret_cast<const double2*>(Ar + mt * 8 * KS + s16 * 16 + 2);
+                const double* row = Ks + s16 * (RT * 16) + (warp * 16 + mt * 8 + g) * 16;
+                const double2 lo = *reinterpret_cast<const double2*>(row + off0);
+                const double2 hi = *reinterpret_cast<const double2*>(row + off1);
                 a[mt][0] = lo.x; a[mt][1] = lo.y; a[mt][2] = hi.x; a[mt][3] = hi.y;
             }
 #pragma unroll
             for (int nt = 0; nt < NB; ++nt) {
-                const double2 lo = *reinterpret_cast<const double2*>(Br + nt * 8 * KS + s16 * 16);
-                const double2 hi = *reinterpret_cast<const double2*>(Br + nt * 8 * KS + s16 * 16 + 2);
+                const double* row = Vs + s16 * (NB * 8 * 16) + (nt * 8 + g) * 16;
+                const double2 lo = *reinterpret_cast<const double2*>(row + off0);
+                const double2 hi = *reinterpret_cast<const double2*>(row + off1);
                 b[nt][0] = lo.x; b[nt][1] = lo.y; b[nt][2] = hi.x; b[nt][3] = hi.y;
             }
 #pragma unroll
@@ -100,8 +148,8 @@ __global__ void __launch_bounds__(256, 1) symm_dmma_kernel(const SymmParams p) {
                     for (int nt = 0; nt < NB; ++nt)
                         dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt][e], b[nt][e]);
         }
-        __syncthreads();
-        if (ci + 2 < nc) issue(ci + 2, s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
     }
 
     double* Y = p.Yp + (long)ks * p.bcols * p.rows_pad;
@@ -126,30 +174,33 @@ __global__ void symm_reduce_kernel(const double* __restrict__ Yp, int splits, lo
 }
 
 // naive cross-check: one thread per (row, col)
-__global__ void symm_naive_kernel(const SymmParams p, double* Y) {
+__global__ void symm_naive_kernel(const double* K, long ldk, const double* V, long ldr, long v_rank_stride,
+                                  long rows_pad, long ncols, double* Y) {
     const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
-    if (row >= p.rows_pad) return;
-    const long ncols = (long)p.nchunks * BKC;
+    if (row >= rows_pad) return;
     double s = 0.0;
     for (long j = 0; j < ncols; ++j) {
-        const long rk = j / p.ldr;
-        s += p.K[row * p.ldk + j] * p.V[rk * p.v_rank_stride + (long)c * p.ldr + (j - rk * p.ldr)];
+        const long rk = j / ldr;
+        s += K[row * ldk + j] * V[rk * v_rank_stride + (long)c * ldr + (j - rk * ldr)];
     }
-    Y[(long)c * p.rows_pad + row] = s;
+    Y[(long)c * rows_pad + row] = s;
 }
 
 template <int NB>
-int launch_nb(fx_ctx* ctx, const SymmParams& p) {
-    constexpr int STAGE_D = (RT + NB * 8) * KS;
-    constexpr int SMEM = NSTAGE * STAGE_D * 8 + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FX_CUDA(cudaFuncSetAttribute(symm_dmma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
+int launch_nb(fx_ctx* ctx, const CUtensorMap& tmK, const CUtensorMap& tmV, SymmParams p) {
+    constexpr int STAGE_BYTES = RT * BKC * 8 + NB * 8 * BKC * 8;
+    int ns = (227 * 1024 - 1024 - 128) / STAGE_BYTES;
+    if (ns > 4) ns = 4;
+    p.nstage = ns;
+    const int smem = ns * STAGE_BYTES + 1024 + 128;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        FX_CUDA(cudaFuncSetAttribute(symm_dmma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
     }
     const unsigned grid = (unsigned)((p.rows_pad / RT) * p.splits);
-    symm_dmma_kernel<NB><<<grid, 256, SMEM, ctx->stream>>>(p);
+    symm_dmma_kernel<NB><<<grid, 288, smem, ctx->stream>>>(tmK, tmV, p);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;
@@ -180,27 +231,55 @@ int fx_launch_symm(fx_ctx* ctx, const SymmArgs& a, int variant) {
         return FX_ERR_CUDA;
     }
     if (a.rows_pad == 0) return 0;
-    SymmParams p;
-    p.K = a.K; p.ldk = a.ldk; p.rows_pad = a.rows_pad; p.V = a.V; p.ldr = a.ldr;
-    p.v_rank_stride = a.v_rank_stride; p.nchunks = (int)(a.ldk / BKC); p.bcols = a.bcols;
-    p.splits = a.splits < 1 ? 1 : a.splits;
     if (variant != 0) {
         dim3 grid((unsigned)ceil_div(a.rows_pad, 128), (unsigned)a.bcols);
-        symm_naive_kernel<<<grid, 128, 0, ctx->stream>>>(p, a.Y);
+        symm_naive_kernel<<<grid, 128, 0, ctx->stream>>>(a.K, a.ldk, a.V, a.ldr, a.v_rank_stride, a.rows_pad,
+                                                         a.ldk, a.Y);
         ctx->launches++;
         FX_LAUNCH_CHECK();
         return 0;
     }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        fx_set_error("symm: cuTensorMapEncodeTiled is not available from this driver");
+        return FX_ERR_CUDA;
+    }
+    CUtensorMap tmK, tmV;
+    {
+        cuuint64_t dims[3] = {16, (cuuint64_t)a.rows_pad, (cuuint64_t)(a.ldk / 16)};
+        cuuint64_t strides[2] = {(cuuint64_t)a.ldk * 8, 128};
+        cuuint32_t box[3] = {16, RT, BKC / 16};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)a.K, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { fx_set_error("symm: tensor map for K rejected (CUresult %d)", (int)r); return FX_ERR_CUDA; }
+    }
+    {
+        const int64_t nranks = a.ldk / a.ldr;
+        cuuint64_t dims[4] = {16, (cuuint64_t)a.bcols, (cuuint64_t)(a.ldr / 16), (cuuint64_t)nranks};
+        cuuint64_t strides[3] = {(cuuint64_t)a.ldr * 8, 128, (cuuint64_t)a.v_rank_stride * 8};
+        cuuint32_t box[4] = {16, (cuuint32_t)a.bcols, BKC / 16, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmV, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)a.V, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { fx_set_error("symm: tensor map for V rejected (CUresult %d)", (int)r); return FX_ERR_CUDA; }
+    }
+    SymmParams p;
+    p.rows_pad = a.rows_pad; p.ldr = a.ldr; p.nchunks = (int)(a.ldk / BKC); p.bcols = a.bcols;
+    p.splits = a.splits < 1 ? 1 : a.splits;
     p.Yp = (p.splits == 1) ? a.Y : a.Ypart;
+    p.nstage = 2;
     switch (a.bcols / 8) {
-        case 1: FX_TRY(launch_nb<1>(ctx, p)); break;
-        case 2: FX_TRY(launch_nb<2>(ctx, p)); break;
-        case 3: FX_TRY(launch_nb<3>(ctx, p)); break;
-        case 4: FX_TRY(launch_nb<4>(ctx, p)); break;
-        case 5: FX_TRY(launch_nb<5>(ctx, p)); break;
-        case 6: FX_TRY(launch_nb<6>(ctx, p)); break;
-        case 7: FX_TRY(launch_nb<7>(ctx, p)); break;
-        default: FX_TRY(launch_nb<8>(ctx, p)); break;
+        case 1: FX_TRY(launch_nb<1>(ctx, tmK, tmV, p)); break;
+        case 2: FX_TRY(launch_nb<2>(ctx, tmK, tmV, p)); break;
+        case 3: FX_TRY(launch_nb<3>(ctx, tmK, tmV, p)); break;
+        case 4: FX_TRY(launch_nb<4>(ctx, tmK, tmV, p)); break;
+        case 5: FX_TRY(launch_nb<5>(ctx, tmK, tmV, p)); break;
+        case 6: FX_TRY(launch_nb<6>(ctx, tmK, tmV, p)); break;
+        case 7: FX_TRY(launch_nb<7>(ctx, tmK, tmV, p)); break;
+        default: FX_TRY(launch_nb<8>(ctx, tmK, tmV, p)); break;
     }
     if (p.splits > 1) {
         const long total = (long)a.bcols * a.rows_pad;

@@ -30,7 +30,7 @@ struct TrParams {
     KernelMap km;
 };
 
-template <int NBK>
+template <int NBK, int KID>
 __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nk = 0; nk < NBK; ++nk) acc2[mt][nk][0] = acc2[mt][nk][1] = 0.0;
-    const bool gauss = p.km.id == FX_KERNEL_GAUSSIAN;
+    constexpr bool gauss = (KID == 0);
     double nzr[2] = {0.0, 0.0};
     if (gauss) {
         nzr[0] = p.nz[q0 + warp * 16 + g];
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
             const bool v0 = j < p.n_valid, v1 = (j + 1) < p.n_valid;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                acc1[mt][nt][0] = v0 ? kernel_map(p.km, acc1[mt][nt][0], nzr[mt], nx0, false) : 0.0;
-                acc1[mt][nt][1] = v1 ? kernel_map(p.km, acc1[mt][nt][1], nzr[mt], nx1, false) : 0.0;
+                acc1[mt][nt][0] = v0 ? kernel_map_t<KID>(p.km, acc1[mt][nt][0], nzr[mt], nx0, false) : 0.0;
+                acc1[mt][nt][1] = v1 ? kernel_map_t<KID>(p.km, acc1[mt][nt][1], nzr[mt], nx1, false) : 0.0;
             }
         }
 
@@ -203,19 +203,28 @@ __global__ void transform_naive_kernel(const TrParams p, int d_pad, long m_pad) 
     p.out[(long)c * p.ldo + q] = s - (p.bias ? p.bias[c] : 0.0);
 }
 
-template <int NBK>
-int launch_tr(fx_ctx* ctx, const TrParams& p, long m_pad) {
+template <int NBK, int KID>
+int launch_tr2(fx_ctx* ctx, const TrParams& p, long m_pad) {
     constexpr int SMEM = (TST * TSTAGE_D + 2 * NBK * 8 * WS) * 8 + 128;
     static bool attr_set = false;
     if (!attr_set) {
-        FX_CUDA(cudaFuncSetAttribute(transform_kernel<NBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        FX_CUDA(cudaFuncSetAttribute(transform_kernel<NBK, KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
     dim3 grid((unsigned)(m_pad / TQ), (unsigned)p.nsplit);
-    transform_kernel<NBK><<<grid, 288, SMEM, ctx->stream>>>(p);
+    transform_kernel<NBK, KID><<<grid, 288, SMEM, ctx->stream>>>(p);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;
+}
+template <int NBK>
+int launch_tr(fx_ctx* ctx, const TrParams& p, long m_pad) {
+    switch (kernel_variant(p.km.id, p.km.ipow)) {
+        case 0: return launch_tr2<NBK, 0>(ctx, p, m_pad);
+        case 1: return launch_tr2<NBK, 1>(ctx, p, m_pad);
+        case 2: return launch_tr2<NBK, 2>(ctx, p, m_pad);
+        default: return launch_tr2<NBK, 3>(ctx, p, m_pad);
+    }
 }
 
 }  // namespace
