@@ -2,14 +2,16 @@
 // per-tile row sums fused into the epilogue.  Replaces MLKernels.kernelmatrix as called at
 // /root/reference/src/kpca.jl:51 (symmetric) and kpca.jl:65 (cross).
 //
-// Data path (per 128x64 output tile; 4 MMA warps + 1 producer warp; 2 CTAs/SM):
-//   producer warp: HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 4-stage
-//     smem ring of 16-feature slabs (no CTA-wide barrier in the main loop)
-//   MMA warps: LDS.64 conflict-free (row stride = 4 mod 16 doubles) --> DMMA.8x8x4
-//     (mma.sync f64), 64x32 register tile per warp
+// Data path (persistent CTAs, 2 per SM, each looping over 128x64 output tiles):
+//   producer warpgroup (one active warp; gives its registers to the MMA warps via setmaxnreg):
+//     HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 4-stage smem ring of
+//     16-feature slabs; it runs ahead across tile boundaries, so the next tile's first slabs
+//     land while the MMA warps are still in the epilogue of the previous one
+//   4 MMA warps: LDS.64 conflict-free (row stride = 4 mod 16 doubles) --> DMMA.8x8x4
+//     (mma.sync f64), 64x32 register tile per warp, no CTA-wide barrier in the main loop
 //   epilogue: kernel map applied IN REGISTERS (64 independent elements per thread, branch-free
-//     exp) --> row sums by 2-step warp shuffle --> smem staging --> 16-byte coalesced stores
-//     (a warp writes 512 contiguous bytes of one K row).
+//     exp) --> row sums by 2-step warp shuffle --> 16-byte stores straight from the accumulator
+//     fragments (one store instruction covers 8 rows x 64 contiguous bytes = 16 full sectors).
 #include "fx_kernels.cuh"
 
 namespace {
@@ -18,9 +20,7 @@ constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
 constexpr int AS = BM + 4;                      // 132: (t*AS + g) mod 16 distinct for t,g in 0..3
 constexpr int BS = BN + 4;                      // 68
 constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25600 B)
-constexpr int CS = 72;                          // staging row stride (conflict-free STS.128)
-constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 2 * BM * 8 + 128;
-static_assert(BM * CS <= STAGES * STAGE_D, "staging tile must fit in the pipeline buffers");
+constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 2 * 2 * BM * 8 + 128;
 
 struct GramParams {
     const double* A; long lda;
@@ -30,6 +30,7 @@ struct GramParams {
     double* rowpart; long rows_pad;
     long rows_valid, cols_valid, diag_shift;
     int kt;
+    int tiles_x; long tiles_total;
     KernelMap km;
 };
 
@@ -39,14 +40,12 @@ template <int KID>
 __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
-    double* rs = smem + (size_t)STAGES * STAGE_D;                  // [2][BM] row-sum halves
-    uint64_t* full = reinterpret_cast<uint64_t*>(rs + 2 * BM);
+    double* rs = smem + (size_t)STAGES * STAGE_D;                  // [2 bufs][2 halves][BM]
+    uint64_t* full = reinterpret_cast<uint64_t*>(rs + 4 * BM);
     uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const long i0 = (long)blockIdx.y * BM;
-    const long j0 = (long)blockIdx.x * BN;
     const int KT = p.kt;
 
     if (tid == 0) {
@@ -60,18 +59,22 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         // ---------------- producer warpgroup: hands its registers to the MMA warps ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp != 4) return;
-        for (int kt = 0; kt < KT; ++kt) {
-            const int s = kt % STAGES;
-            mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);        // passes at once on first use
-            double* As = smem + (size_t)s * STAGE_D;
-            double* Bs = As + BK * AS;
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], BK * (BM + BN) * 8);
-            __syncwarp();
-            if (lane < BK)
-                bulk_g2s(As + lane * AS, p.A + (long)(kt * BK + lane) * p.lda + i0, BM * 8, &full[s]);
-            else
-                bulk_g2s(Bs + (lane - BK) * BS, p.B + (long)(kt * BK + lane - BK) * p.ldb + j0, BN * 8,
-                         &full[s]);
+        int it = 0;
+        for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            const long i0 = (tile / p.tiles_x) * BM, j0 = (tile % p.tiles_x) * BN;
+            for (int kt = 0; kt < KT; ++kt, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);    // passes at once on first use
+                double* As = smem + (size_t)s * STAGE_D;
+                double* Bs = As + BK * AS;
+                if (lane == 0) mbar_arrive_expect_tx(&full[s], BK * (BM + BN) * 8);
+                __syncwarp();
+                if (lane < BK)
+                    bulk_g2s(As + lane * AS, p.A + (long)(kt * BK + lane) * p.lda + i0, BM * 8, &full[s]);
+                else
+                    bulk_g2s(Bs + (lane - BK) * BS, p.B + (long)(kt * BK + lane - BK) * p.ldb + j0, BN * 8,
+                             &full[s]);
+            }
         }
         return;
     }
@@ -79,93 +82,81 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     // -------------------------------- MMA warps --------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int wm = warp >> 1, wn = warp & 1;
-    double acc[8][4][2];
+    int it = 0, tcount = 0;
+    for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tcount) {
+        const long i0 = (tile / p.tiles_x) * BM, j0 = (tile % p.tiles_x) * BN;
+        double acc[8][4][2];
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
+        for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % STAGES;
-        mbar_wait(&full[s], (kt / STAGES) & 1);
-        const double* As = smem + (size_t)s * STAGE_D + wm * 64 + g;
-        const double* Bs = smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            const double* As = smem + (size_t)s * STAGE_D + wm * 64 + g;
+            const double* Bs = smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g;
 #pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            double a[8], b[4];
-            const int kr = kk * 4 + t;
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                double a[8], b[4];
+                const int kr = kk * 4 + t;
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * AS + mt * 8];
+                for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * AS + mt * 8];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * BS + nt * 8];
+                for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * BS + nt * 8];
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt)
+                for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+                    for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);               // this warp is done with stage s
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);                   // this warp is done with stage s
-    }
 
-    // ---- epilogue: map in registers, shuffle row sums, stage through smem, coalesced stores ----
-    double nbv[4][2];
-    bool jv[4][2];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        const long j = j0 + wn * 32 + nt * 8 + 2 * t;
-        jv[nt][0] = j < p.cols_valid;
-        jv[nt][1] = (j + 1) < p.cols_valid;
-        nbv[nt][0] = nbv[nt][1] = 0.0;
-        if (KID == 0) {
-            const double2 v = *reinterpret_cast<const double2*>(p.nb + j);
-            nbv[nt][0] = v.x; nbv[nt][1] = v.y;
-        }
-    }
-    double rsum[8];
-#pragma unroll
-    for (int mt = 0; mt < 8; ++mt) {
-        const long i = i0 + wm * 64 + mt * 8 + g;
-        const bool iv = i < p.rows_valid;
-        const double ni = (KID == 0) ? p.na[i] : 0.0;
-        const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
-        double sacc = 0.0;
+        // ---- epilogue: map in registers, shuffle row sums, direct 16-byte stores ----
+        double nbv[4][2];
+        bool jv[4][2];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             const long j = j0 + wn * 32 + nt * 8 + 2 * t;
-            const double v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni, nbv[nt][0], ig == j);
-            const double v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni, nbv[nt][1], ig == j + 1);
-            acc[mt][nt][0] = (iv && jv[nt][0]) ? v0 : 0.0;
-            acc[mt][nt][1] = (iv && jv[nt][1]) ? v1 : 0.0;
-            sacc += acc[mt][nt][0] + acc[mt][nt][1];
+            jv[nt][0] = j < p.cols_valid;
+            jv[nt][1] = (j + 1) < p.cols_valid;
+            nbv[nt][0] = nbv[nt][1] = 0.0;
+            if (KID == 0) {
+                const double2 v = *reinterpret_cast<const double2*>(p.nb + j);
+                nbv[nt][0] = v.x; nbv[nt][1] = v.y;
+            }
         }
-        rsum[mt] = sacc;
-    }
-    if (p.rowpart) {
+        double* rsb = rs + (tcount & 1) * 2 * BM;
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt) {
-            double v = rsum[mt];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (t == 0) rs[wn * BM + wm * 64 + mt * 8 + g] = v;
+            const long i = i0 + wm * 64 + mt * 8 + g;
+            const bool iv = i < p.rows_valid;
+            const double ni = (KID == 0) ? p.na[i] : 0.0;
+            const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+            double* krow = p.K + i * p.ldk + j0 + wn * 32 + 2 * t;
+            double sacc = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const long j = j0 + wn * 32 + nt * 8 + 2 * t;
+                double v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni, nbv[nt][0], ig == j);
+                double v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni, nbv[nt][1], ig == j + 1);
+                v0 = (iv && jv[nt][0]) ? v0 : 0.0;
+                v1 = (iv && jv[nt][1]) ? v1 : 0.0;
+                *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(v0, v1);
+                sacc += v0 + v1;
+            }
+            if (p.rowpart) {
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = sacc;
+            }
+        }
+        if (p.rowpart) {
+            bar_sync_compute();                  // both column halves of every row are in smem
+            p.rowpart[(tile % p.tiles_x) * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
         }
     }
-    bar_sync_compute();                          // every MMA warp is done reading the ring
-    double* Cs = smem;
-#pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const int r = wm * 64 + mt * 8 + g, c = wn * 32 + nt * 8 + 2 * t;
-            *reinterpret_cast<double2*>(&Cs[r * CS + c]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-        }
-    bar_sync_compute();
-    double* Kout = p.K + (i0 + warp * 32) * p.ldk + j0 + 2 * lane;
-    const double* Crow = Cs + (warp * 32) * CS + 2 * lane;
-#pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr)
-        *reinterpret_cast<double2*>(Kout + (long)rr * p.ldk) = *reinterpret_cast<const double2*>(Crow + rr * CS);
-    if (p.rowpart && tid < BM)
-        p.rowpart[(long)blockIdx.x * p.rows_pad + i0 + tid] = rs[tid] + rs[BM + tid];
 }
 
 // ---- naive cross-check variant: one thread per output element -------------------------------
@@ -227,6 +218,8 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     p.K = a.K; p.ldk = a.ldk; p.rowpart = a.rowpart; p.rows_pad = a.rows_pad;
     p.rows_valid = a.rows_valid; p.cols_valid = a.cols_valid; p.diag_shift = a.diag_shift;
     p.kt = (int)(a.d_pad / BK);
+    p.tiles_x = (int)(a.ldk / BN);
+    p.tiles_total = (long)(a.ldk / BN) * (a.rows_pad / BM);
     p.km.id = a.kernel_id; p.km.p0 = a.kp[0]; p.km.p1 = a.kp[1]; p.km.p2 = a.kp[2];
     double tmp[3];
     if (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp)) {
@@ -243,7 +236,8 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             attr_set = true;
         }
-        dim3 grid((unsigned)(a.ldk / BN), (unsigned)(a.rows_pad / BM));
+        long want = 2L * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+        const unsigned grid = (unsigned)(p.tiles_total < want ? p.tiles_total : want);
         switch (kernel_variant(p.km.id, p.km.ipow)) {
             case 0: gram_dmma_kernel<0><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
             case 1: gram_dmma_kernel<1><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
