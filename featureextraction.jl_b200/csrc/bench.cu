@@ -40,6 +40,39 @@ __global__ void dmma_sweep_kernel(double* out, int iters) {
     if (s == 123.456) out[0] = s;
 }
 
+// do DMMA and DFMA share the FP64 datapath?  warps 0-3 run DMMA chains, warps 4-7 DFMA chains;
+// mode 0: DMMA only, 1: DFMA only, 2: both concurrently
+__global__ void __launch_bounds__(256) fp64_share_kernel(double* out, int iters, int mode) {
+    const int warp = threadIdx.x >> 5;
+    double s = 0.0;
+    if (warp < 4) {
+        if (mode == 1) return;
+        double c[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+        double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma(c[i][0], c[i][1], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    } else {
+        if (mode == 0) return;
+        double c[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-3 + i;
+        const double a = 1.0000001, b = 1e-9;
+        for (int it = 0; it < iters * 8; ++it) {           // 8*16 DFMA per DMMA-iteration: equal lane-cycles
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += c[i];
+    }
+    if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
     double c[16];
 #pragma unroll
@@ -112,6 +145,18 @@ extern "C" int fx_bench_kernel(fx_ctx* ctx, int which, int64_t n, int64_t d, int
         return time_loop(ctx, reps, ms_out, [&]() -> int {
             if (which == 4) dmma_peak_kernel<<<grid, 256, 0, s>>>(out, iters);
             else dfma_peak_kernel<<<grid, 256, 0, s>>>(out, iters);
+            ctx->launches++;
+            FX_LAUNCH_CHECK();
+            return 0;
+        });
+    }
+    if (which == 8) {
+        FX_TRY(fx_arena_reserve(ctx, 4096));
+        fx_arena_reset(ctx);
+        double* out = (double*)fx_arena_alloc(ctx, 256);
+        const int mode = (int)d, iters = 4000;
+        return time_loop(ctx, reps, ms_out, [&]() -> int {
+            fp64_share_kernel<<<ctx->sm_count, 256, 0, s>>>(out, iters, mode);
             ctx->launches++;
             FX_LAUNCH_CHECK();
             return 0;

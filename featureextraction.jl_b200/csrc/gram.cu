@@ -31,6 +31,7 @@ struct GramParams {
     long rows_valid, cols_valid, diag_shift;
     int kt;
     int tiles_x; long tiles_total;
+    int* sm_slots; long long phase_delay;   // second CTA of an SM starts half a tile late
     KernelMap km;
 };
 
@@ -48,10 +49,21 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     const int g = lane >> 2, t = lane & 3;
     const int KT = p.kt;
 
+    __shared__ int s_slot;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
         fence_mbar_init();
+        // The two CTAs of an SM would otherwise run their main loops and their epilogues in
+        // lock-step (identical tiles): stagger the second one by half a tile so one CTA's
+        // epilogue overlaps the other's DMMA stream.
+        int slot = 0;
+        if (p.sm_slots && p.phase_delay > 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            slot = atomicAdd(&p.sm_slots[smid & 1023], 1) & 1;
+        }
+        s_slot = slot;
     }
     __syncthreads();
 
@@ -82,6 +94,10 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     // -------------------------------- MMA warps --------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int wm = warp >> 1, wn = warp & 1;
+    if (s_slot) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.phase_delay) __nanosleep(200);
+    }
     int it = 0, tcount = 0;
     for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tcount) {
         const long i0 = (tile / p.tiles_x) * BM, j0 = (tile % p.tiles_x) * BN;
@@ -238,6 +254,14 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
         }
         long want = 2L * (ctx->sm_count > 0 ? ctx->sm_count : 148);
         const unsigned grid = (unsigned)(p.tiles_total < want ? p.tiles_total : want);
+        p.sm_slots = nullptr;
+        p.phase_delay = 0;
+        if (p.tiles_total >= 3 * want) {
+            if (!ctx->sm_slots) FX_CUDA(cudaMalloc((void**)&ctx->sm_slots, 1024 * sizeof(int)));
+            FX_CUDA(cudaMemsetAsync(ctx->sm_slots, 0, 1024 * sizeof(int), ctx->stream));
+            p.sm_slots = ctx->sm_slots;
+            p.phase_delay = (long long)p.kt * 2100 + 3000;      // ~half a tile in SM cycles
+        }
         switch (kernel_variant(p.km.id, p.km.ipow)) {
             case 0: gram_dmma_kernel<0><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
             case 1: gram_dmma_kernel<1><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;

@@ -166,7 +166,8 @@ int fx_syevd_small_f64(fx_ctx* ctx, double* A, int m, int64_t lda, double* w, in
 /* Times `reps` launches of one kernel class with CUDA events on the context stream:
  *   which = 0 Gram(+epilogue), 1 centering, 2 K*V, 3 fused transform, 4 DMMA issue-rate
  *   microbenchmark (register-only), 5 DFMA issue-rate microbenchmark, 6 stream copy,
- *           7 DMMA issue sweep (n = CTAs/SM, b = warps/CTA, d = accumulators/warp, m = iters).
+ *           7 DMMA issue sweep (n = CTAs/SM, b = warps/CTA, d = accumulators/warp, m = iters),
+ *           8 DMMA/DFMA datapath sharing probe (d = 0 DMMA only, 1 DFMA only, 2 both).
  * Sizes: n rows, d features, b block width / components, m queries.  ms_out[reps].  */
 int fx_bench_kernel(fx_ctx* ctx, int which, int64_t n, int64_t d, int b, int64_t m,
                     int kernel_id, int reps, double* ms_out);
