@@ -63,7 +63,6 @@ struct fx_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     int64_t launches = 0;
-    int* sm_slots = nullptr;      // per-SM CTA arrival counters (Gram anti-phase start)
 };
 
 // Arena: reserve() guarantees capacity (may re-allocate: only legal when nothing is live),

@@ -31,11 +31,49 @@ struct GramParams {
     long rows_valid, cols_valid, diag_shift;
     int kt;
     int tiles_x; long tiles_total;
-    int* sm_slots; long long phase_delay;   // second CTA of an SM starts half a tile late
     KernelMap km;
 };
 
 __device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Kernel map + row sums + stores for one warp's 64x32 accumulator tile.  EDGE tiles (ragged
+// borders or touching the diagonal) carry the validity masks and the same-point test; interior
+// tiles run the bare arithmetic.
+template <int KID, bool EDGE>
+__device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[8][4][2],
+                                              const double (&ni)[8], const double (&nbv)[4][2], long i0,
+                                              long j0, int wm, int wn, int g, int t, double* rsb) {
+    const long jb = j0 + wn * 32 + 2 * t;
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+        const long i = i0 + wm * 64 + mt * 8 + g;
+        double* krow = p.K + i * p.ldk + jb;
+        const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+        const bool iv = i < p.rows_valid;
+        double sacc = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            double v0, v1;
+            if (EDGE) {
+                const long j = jb + nt * 8;
+                v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], ig == j);
+                v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], ig == j + 1);
+                v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
+                v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
+            } else {
+                v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], false);
+                v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], false);
+            }
+            *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(v0, v1);
+            sacc += v0 + v1;
+        }
+        if (p.rowpart) {
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = sacc;
+        }
+    }
+}
 
 template <int KID>
 __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
@@ -49,21 +87,10 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     const int g = lane >> 2, t = lane & 3;
     const int KT = p.kt;
 
-    __shared__ int s_slot;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
         fence_mbar_init();
-        // The two CTAs of an SM would otherwise run their main loops and their epilogues in
-        // lock-step (identical tiles): stagger the second one by half a tile so one CTA's
-        // epilogue overlaps the other's DMMA stream.
-        int slot = 0;
-        if (p.sm_slots && p.phase_delay > 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            slot = atomicAdd(&p.sm_slots[smid & 1023], 1) & 1;
-        }
-        s_slot = slot;
     }
     __syncthreads();
 
@@ -94,10 +121,6 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     // -------------------------------- MMA warps --------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int wm = warp >> 1, wn = warp & 1;
-    if (s_slot) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < p.phase_delay) __nanosleep(200);
-    }
     int it = 0, tcount = 0;
     for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tcount) {
         const long i0 = (tile / p.tiles_x) * BM, j0 = (tile % p.tiles_x) * BN;
@@ -106,6 +129,18 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        // squared norms for the Gaussian map: requested now, consumed after the main loop
+        double ni[8], nbv[4][2];
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) ni[mt] = (KID == 0) ? p.na[i0 + wm * 64 + mt * 8 + g] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            nbv[nt][0] = nbv[nt][1] = 0.0;
+            if (KID == 0) {
+                const double2 v = *reinterpret_cast<const double2*>(p.nb + j0 + wn * 32 + nt * 8 + 2 * t);
+                nbv[nt][0] = v.x; nbv[nt][1] = v.y;
+            }
+        }
 
         for (int kt = 0; kt < KT; ++kt, ++it) {
             const int s = it % STAGES;
@@ -130,44 +165,12 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         }
 
         // ---- epilogue: map in registers, shuffle row sums, direct 16-byte stores ----
-        double nbv[4][2];
-        bool jv[4][2];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const long j = j0 + wn * 32 + nt * 8 + 2 * t;
-            jv[nt][0] = j < p.cols_valid;
-            jv[nt][1] = (j + 1) < p.cols_valid;
-            nbv[nt][0] = nbv[nt][1] = 0.0;
-            if (KID == 0) {
-                const double2 v = *reinterpret_cast<const double2*>(p.nb + j);
-                nbv[nt][0] = v.x; nbv[nt][1] = v.y;
-            }
-        }
         double* rsb = rs + (tcount & 1) * 2 * BM;
-#pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
-            const long i = i0 + wm * 64 + mt * 8 + g;
-            const bool iv = i < p.rows_valid;
-            const double ni = (KID == 0) ? p.na[i] : 0.0;
-            const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
-            double* krow = p.K + i * p.ldk + j0 + wn * 32 + 2 * t;
-            double sacc = 0.0;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const long j = j0 + wn * 32 + nt * 8 + 2 * t;
-                double v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni, nbv[nt][0], ig == j);
-                double v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni, nbv[nt][1], ig == j + 1);
-                v0 = (iv && jv[nt][0]) ? v0 : 0.0;
-                v1 = (iv && jv[nt][1]) ? v1 : 0.0;
-                *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(v0, v1);
-                sacc += v0 + v1;
-            }
-            if (p.rowpart) {
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-                if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = sacc;
-            }
-        }
+        const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
+        const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
+                          (ig0 < j0 + BN && ig0 + BM > j0);
+        if (edge) gram_epilogue<KID, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+        else      gram_epilogue<KID, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
         if (p.rowpart) {
             bar_sync_compute();                  // both column halves of every row are in smem
             p.rowpart[(tile % p.tiles_x) * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
@@ -254,14 +257,6 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
         }
         long want = 2L * (ctx->sm_count > 0 ? ctx->sm_count : 148);
         const unsigned grid = (unsigned)(p.tiles_total < want ? p.tiles_total : want);
-        p.sm_slots = nullptr;
-        p.phase_delay = 0;
-        if (p.tiles_total >= 3 * want) {
-            if (!ctx->sm_slots) FX_CUDA(cudaMalloc((void**)&ctx->sm_slots, 1024 * sizeof(int)));
-            FX_CUDA(cudaMemsetAsync(ctx->sm_slots, 0, 1024 * sizeof(int), ctx->stream));
-            p.sm_slots = ctx->sm_slots;
-            p.phase_delay = (long long)p.kt * 2100 + 3000;      // ~half a tile in SM cycles
-        }
         switch (kernel_variant(p.km.id, p.km.ipow)) {
             case 0: gram_dmma_kernel<0><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
             case 1: gram_dmma_kernel<1><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
