@@ -2,17 +2,13 @@
 // per-tile row sums fused into the epilogue.  Replaces MLKernels.kernelmatrix as called at
 // /root/reference/src/kpca.jl:51 (symmetric) and kpca.jl:65 (cross).
 //
-// Data path (persistent, one CTA per SM, 12 warps):
-//   producer warpgroup (one active warp; hands its registers to the MMA warps via setmaxnreg):
-//     HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 6-stage smem ring of
-//     16-feature slabs, running ahead across tile boundaries
-//   two MMA groups of 4 warps in PING-PONG (named barriers): while one group streams DMMA.8x8x4
-//     (mma.sync f64) through a 128x64 tile -- LDS.64 conflict-free fragments (row stride = 4 mod
-//     16 doubles), double-buffered in registers across stage boundaries -- the other group runs
-//     the epilogue of its previous tile.  DMMA and DFMA share one FP64 datapath on B200
-//     (profiles/r01_fp64_datapath_sharing.txt), so the epilogue's exp() can only fill issue gaps;
-//     the ping-pong keeps the DMMA stream of exactly one group on the pipe at any time and
-//     stops the two tile streams from falling into lock-step.
+// Data path (persistent CTAs, 2 per SM, each looping over 128x64 output tiles):
+//   producer warpgroup (one active warp; gives its registers to the MMA warps via setmaxnreg):
+//     HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 4-stage smem ring of
+//     16-feature slabs; it runs ahead across tile boundaries, so the next tile's first slabs
+//     land while the MMA warps are still in the epilogue of the previous one
+//   4 MMA warps: LDS.64 conflict-free (row stride = 4 mod 16 doubles) --> DMMA.8x8x4
+//     (mma.sync f64), 64x32 register tile per warp, no CTA-wide barrier in the main loop
 //   epilogue: kernel map applied IN REGISTERS (64 independent elements per thread, branch-free
 //     exp) --> row sums by 2-step warp shuffle --> 16-byte stores straight from the accumulator
 //     fragments (one store instruction covers 8 rows x 64 contiguous bytes = 16 full sectors).
@@ -20,12 +16,11 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 6;
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
 constexpr int AS = BM + 4;                      // 132: (t*AS + g) mod 16 distinct for t,g in 0..3
 constexpr int BS = BN + 4;                      // 68
 constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25600 B)
-constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 2 * 2 * 2 * BM * 8 + 256;
-constexpr int NTHREADS = 384;
+constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 2 * 2 * BM * 8 + 128;
 
 struct GramParams {
     const double* A; long lda;
@@ -39,31 +34,16 @@ struct GramParams {
     KernelMap km;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int n) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int n) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
+__device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Kernel map + row sums + stores for one warp's 64x32 accumulator tile.  EDGE tiles (ragged
 // borders or touching the diagonal) carry the validity masks and the same-point test; interior
 // tiles run the bare arithmetic.
 template <int KID, bool EDGE>
-__device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[8][4][2], long i0, long j0,
-                                              int wm, int wn, int g, int t, double* rsb) {
+__device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[8][4][2],
+                                              const double (&ni)[8], const double (&nbv)[4][2], long i0,
+                                              long j0, int wm, int wn, int g, int t, double* rsb) {
     const long jb = j0 + wn * 32 + 2 * t;
-    double ni[8], nbv[4][2];
-#pragma unroll
-    for (int mt = 0; mt < 8; ++mt) ni[mt] = (KID == 0) ? p.na[i0 + wm * 64 + mt * 8 + g] : 0.0;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        nbv[nt][0] = nbv[nt][1] = 0.0;
-        if (KID == 0) {
-            const double2 v = *reinterpret_cast<const double2*>(p.nb + jb + nt * 8);
-            nbv[nt][0] = v.x; nbv[nt][1] = v.y;
-        }
-    }
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) {
         const long i = i0 + wm * 64 + mt * 8 + g;
@@ -95,27 +75,17 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
     }
 }
 
-__device__ __forceinline__ void load_frags(double (&a)[8], double (&b)[4], const double* As, const double* Bs,
-                                           int kr) {
-#pragma unroll
-    for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * AS + mt * 8];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * BS + nt * 8];
-}
-
 template <int KID>
-__global__ void __launch_bounds__(NTHREADS, 1) gram_dmma_kernel(const GramParams p) {
+__global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
-    double* rs = smem + (size_t)STAGES * STAGE_D;                  // [2 groups][2 bufs][2 halves][BM]
-    uint64_t* full = reinterpret_cast<uint64_t*>(rs + 8 * BM);
+    double* rs = smem + (size_t)STAGES * STAGE_D;                  // [2 bufs][2 halves][BM]
+    uint64_t* full = reinterpret_cast<uint64_t*>(rs + 4 * BM);
     uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int KT = p.kt;
-    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int nloc = (int)((p.tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     if (tid == 0) {
 #pragma unroll
@@ -124,13 +94,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_dmma_kernel(const GramParams
     }
     __syncthreads();
 
-    if (warp >= 8) {
+    if (warp >= 4) {
         // ---------------- producer warpgroup: hands its registers to the MMA warps ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp != 8) return;
+        if (warp != 4) return;
         int it = 0;
-        for (int l = 0; l < nloc; ++l) {
-            const long tile = blockIdx.x + (long)l * gridDim.x;
+        for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             const long i0 = (tile / p.tiles_x) * BM, j0 = (tile % p.tiles_x) * BN;
             for (int kt = 0; kt < KT; ++kt, ++it) {
                 const int s = it % STAGES;
@@ -149,70 +118,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_dmma_kernel(const GramParams
         return;
     }
 
-    // -------------------------------- MMA warps (two ping-pong groups) --------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int grp = warp >> 2, wl = warp & 3;
-    const int wm = wl >> 1, wn = wl & 1;
-    const int tg = tid & 127;
-    const int iters = (nloc + 1) >> 1;
-    if (grp == 1) named_bar_arrive(1, 256);                       // group 0 owns the pipe first
-    for (int q = 0; q < iters; ++q) {
-        const int l = 2 * q + grp;
-        const bool have = l < nloc;
-        const long tile = blockIdx.x + (long)l * gridDim.x;
+    // -------------------------------- MMA warps --------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int wm = warp >> 1, wn = warp & 1;
+    int it = 0, tcount = 0;
+    for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tcount) {
         const long i0 = (tile / p.tiles_x) * BM, j0 = (tile % p.tiles_x) * BN;
         double acc[8][4][2];
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-
-        named_bar_sync(1 + grp, 256);                             // my turn on the FP64 tensor pipe
-        if (have) {
-            int it = l * KT;
-            int s = it % STAGES;
-            double a[2][8], b[2][4];
-            mbar_wait(&full[s], (it / STAGES) & 1);
-            load_frags(a[0], b[0], smem + (size_t)s * STAGE_D + wm * 64 + g,
-                       smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g, t);
-            for (int kt = 0; kt < KT; ++kt, ++it) {
-                s = it % STAGES;
-                const double* As = smem + (size_t)s * STAGE_D + wm * 64 + g;
-                const double* Bs = smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g;
+        // squared norms for the Gaussian map: requested now, consumed after the main loop
+        double ni[8], nbv[4][2];
 #pragma unroll
-                for (int kk = 0; kk < BK / 4; ++kk) {
-                    const int cur = kk & 1, nxt = cur ^ 1;
-                    if (kk < BK / 4 - 1) {
-                        load_frags(a[nxt], b[nxt], As, Bs, (kk + 1) * 4 + t);
-                    } else if (kt + 1 < KT) {                     // first fragments of the next stage
-                        const int s2 = (it + 1) % STAGES;
-                        mbar_wait(&full[s2], ((it + 1) / STAGES) & 1);
-                        load_frags(a[nxt], b[nxt], smem + (size_t)s2 * STAGE_D + wm * 64 + g,
-                                   smem + (size_t)s2 * STAGE_D + BK * AS + wn * 32 + g, t);
-                    }
+        for (int mt = 0; mt < 8; ++mt) ni[mt] = (KID == 0) ? p.na[i0 + wm * 64 + mt * 8 + g] : 0.0;
 #pragma unroll
-                    for (int mt = 0; mt < 8; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < 4; ++nt)
-                            dmma(acc[mt][nt][0], acc[mt][nt][1], a[cur][mt], b[cur][nt]);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);           // this warp is done with stage s
+        for (int nt = 0; nt < 4; ++nt) {
+            nbv[nt][0] = nbv[nt][1] = 0.0;
+            if (KID == 0) {
+                const double2 v = *reinterpret_cast<const double2*>(p.nb + j0 + wn * 32 + nt * 8 + 2 * t);
+                nbv[nt][0] = v.x; nbv[nt][1] = v.y;
             }
         }
-        if (!(grp == 1 && q == iters - 1)) named_bar_arrive(1 + (grp ^ 1), 256);   // pipe to the other group
 
-        if (have) {
-            double* rsb = rs + (grp * 2 + (q & 1)) * 2 * BM;
-            const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
-            const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
-                              (ig0 < j0 + BN && ig0 + BM > j0);
-            if (edge) gram_epilogue<KID, true>(p, acc, i0, j0, wm, wn, g, t, rsb);
-            else      gram_epilogue<KID, false>(p, acc, i0, j0, wm, wn, g, t, rsb);
-            if (p.rowpart) {
-                named_bar_sync(3 + grp, 128);    // both column halves of every row are in smem
-                p.rowpart[(tile % p.tiles_x) * p.rows_pad + i0 + tg] = rsb[tg] + rsb[BM + tg];
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            const double* As = smem + (size_t)s * STAGE_D + wm * 64 + g;
+            const double* Bs = smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                double a[8], b[4];
+                const int kr = kk * 4 + t;
+#pragma unroll
+                for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * AS + mt * 8];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * BS + nt * 8];
+#pragma unroll
+                for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);               // this warp is done with stage s
+        }
+
+        // ---- epilogue: map in registers, shuffle row sums, direct 16-byte stores ----
+        double* rsb = rs + (tcount & 1) * 2 * BM;
+        const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
+        const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
+                          (ig0 < j0 + BN && ig0 + BM > j0);
+        if (edge) gram_epilogue<KID, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+        else      gram_epilogue<KID, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+        if (p.rowpart) {
+            bar_sync_compute();                  // both column halves of every row are in smem
+            p.rowpart[(tile % p.tiles_x) * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
         }
     }
 }
@@ -294,13 +255,13 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             attr_set = true;
         }
-        long want = (ctx->sm_count > 0 ? ctx->sm_count : 148);
+        long want = 2L * (ctx->sm_count > 0 ? ctx->sm_count : 148);
         const unsigned grid = (unsigned)(p.tiles_total < want ? p.tiles_total : want);
         switch (kernel_variant(p.km.id, p.km.ipow)) {
-            case 0: gram_dmma_kernel<0><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p); break;
-            case 1: gram_dmma_kernel<1><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p); break;
-            case 2: gram_dmma_kernel<2><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p); break;
-            default: gram_dmma_kernel<3><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 0: gram_dmma_kernel<0><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 1: gram_dmma_kernel<1><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 2: gram_dmma_kernel<2><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            default: gram_dmma_kernel<3><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
         }
         ctx->launches++;
     } else {
