@@ -45,13 +45,6 @@ int dmalloc(double** p, size_t doubles) {
 
 }  // namespace
 
-// Shared by KPCA and KLDA fits: pads X into feature-major device storage and builds this rank's
-// row block of K (optionally centred).  All buffers come from the arena (already reserved).
-struct GramStage {
-    int64_t n, d, ld, n_ld, d_pad, row0, rows_valid;
-    double *Xp, *norms, *K, *rowpart, *rowsum, *colmean, *scal;   // scal[0]=grand mean, scal[1]=trace
-};
-
 size_t fx_gramstage_bytes(int64_t ld, int64_t n_ld, int64_t d_pad, bool center) {
     size_t t = 0;
     t += fx_align256((size_t)d_pad * n_ld * 8);

@@ -124,3 +124,16 @@ int fx_launch_copy2d(fx_ctx* ctx, const double* src, int64_t lds, double* dst, i
 size_t fx_transform_scratch(fx_ctx* ctx, int64_t m_pad, int64_t n_ld, int kc, int* nsplit_out);
 int fx_launch_transform_ex(fx_ctx* ctx, const TransformArgs& a, int variant, double* scratch, int nsplit);
 int fx_launch_fill(fx_ctx* ctx, double* p, int64_t n, double v);
+
+// ---- api_kpca.cu: stages shared by the KPCA and KLDA fits ---------------------------------------
+// Pads X into feature-major device storage and builds this rank's row block of K (optionally
+// centred).  All buffers come from the (already reserved) arena.
+struct GramStage {
+    int64_t n, d, ld, n_ld, d_pad, row0, rows_valid;
+    double *Xp, *norms, *K, *rowpart, *rowsum, *colmean, *scal;   // scal[0]=grand mean, scal[1]=trace
+};
+size_t fx_gramstage_bytes(int64_t ld, int64_t n_ld, int64_t d_pad, bool center);
+int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int64_t ldx, int kernel_id,
+                     const double* kp, bool center, int variant, FxTimer& tm, fx_stats* st);
+int fx_model_build(fx_ctx* ctx, const GramStage& g, int kernel_id, const double* kp, int k, const double* W,
+                   bool centered, bool is_klda, fx_model** out);

@@ -1,0 +1,453 @@
+// klda.cu -- Kernel LDA on the KPCA kernels.  The reference's LDA pipeline
+// (/root/reference/src/klda.jl:34-61: class_totals/class_counts -> class means, center_rows!,
+// H_w scaled 1/(n-k), H_b = sqrt(freq) .* (M - mu'), Sigma = syrk + syml!, regularize!/perturb!,
+// generalized symmetric eigenproblem via sygvd) is applied to the kernel matrix K = k(X,X) as
+// the data matrix (`klda!` is exported at FeatureExtraction.jl:11 but never
+// defined and klda.jl:42 passes (Sigma_b, Sigma_b)).  Nothing n x n beyond K is ever formed:
+//   H_b' = K E D  (E = class indicators)                          -> one K*V pass
+//   Sigma_w = K (I - P) K / (n-c)^2,  P = E diag(1/n_c) E'        -> two K*V passes per apply
+//   Sigma_b has rank <= c, so the non-zero pairs of Sigma_b a = l Sigma_w' a come from the c x c
+//   matrix S = H_b Sigma_w'^-1 H_b' (multi-RHS conjugate gradients, columns in lock-step),
+//   a_j = Sigma_w'^-1 H_b' u_j / sqrt(l_j)  so that a' Sigma_w' a = 1 (sygvd itype 1, common.jl:172).
+#include "fx_kernels.cuh"
+#include <math.h>
+
+namespace {
+
+// E in the gathered block layout [rank][col][ldr]: 1 where label == col+1 (grid covers n_ld exactly)
+__global__ void indicator_kernel(const int* __restrict__ y, long n, long ldr, int cp, double* __restrict__ E) {
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;      // global (padded) observation index
+    const int c = blockIdx.y;
+    const long rk = j / ldr;
+    E[(rk * cp + c) * ldr + (j - rk * ldr)] = (j < n && y[j] == c + 1) ? 1.0 : 0.0;
+}
+
+// H_b' rows: hb[i][c] = sqrt(freq_c) (KE[i][c]/n_c - mu_i), mu_i = sum_c freq_c KE[i][c]/n_c
+__global__ void hb_kernel(const double* __restrict__ KE, long ld, long rows_valid, int c, int cp,
+                          const double* __restrict__ freq, const double* __restrict__ inv_cnt,
+                          double* __restrict__ HbT) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    double mu = 0.0;
+    if (i < rows_valid)
+        for (int k = 0; k < c; ++k) mu += freq[k] * KE[(long)k * ld + i] * inv_cnt[k];
+    for (int k = 0; k < cp; ++k) {
+        double v = 0.0;
+        if (i < rows_valid && k < c) v = sqrt(freq[k]) * (KE[(long)k * ld + i] * inv_cnt[k] - mu);
+        HbT[(long)k * ld + i] = v;
+    }
+}
+
+// per local row: sum_j K_ij^2 - sum_c KE[i][c]^2 / n_c   (one warp per row), block-reduced to out[0]
+__global__ void hw_frob_kernel(const double* __restrict__ K, long ldk, long rows_valid, long cols_valid,
+                               const double* __restrict__ KE, long ld, int c,
+                               const double* __restrict__ inv_cnt, double* __restrict__ rowval) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows_valid) return;
+    const double* kr = K + row * ldk;
+    double s = 0.0;
+    for (long j = 2 * lane; j < cols_valid; j += 64) {
+        const double2 v = *reinterpret_cast<const double2*>(kr + j);
+        s = fma(v.x, v.x, s);
+        if (j + 1 < cols_valid) s = fma(v.y, v.y, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        double q = 0.0;
+        for (int k = 0; k < c; ++k) { const double e = KE[(long)k * ld + row]; q += e * e * inv_cnt[k]; }
+        rowval[row] = s - q;
+    }
+}
+__global__ void sum_kernel(const double* __restrict__ v, long n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) *out = t;
+    }
+}
+
+// M = diag(inv_cnt) * S   (cp x cp), zero outside c
+__global__ void scale_rows_kernel(const double* S, const double* inv_cnt, int c, int cp, double* M) {
+    for (int idx = threadIdx.x; idx < cp * cp; idx += blockDim.x) {
+        const int i = idx % cp;
+        M[idx] = (i < c) ? S[idx] * inv_cnt[i] : 0.0;
+    }
+}
+
+// CG bookkeeping, all on the device (single CTA).  state: rs_old[cp], rs0[cp], active[cp]
+// mode 0: init from RR = R'R   -> rs_old = rs0 = diag, active = rs0 > 0
+// mode 1: alpha from PAP       -> Dpos = diag(alpha), Dneg = diag(-alpha)
+// mode 2: beta from new RR     -> Dpos = diag(beta), rs_old = rs_new, active, out[0] = max rel res
+__global__ void cg_scalars_kernel(int mode, const double* Mx, int cp, int c, double* rs_old, double* rs0,
+                                  int* active, double tol, double* Dpos, double* Dneg, double* out) {
+    __shared__ double maxrel;
+    __shared__ int breakdown;
+    if (threadIdx.x == 0) { maxrel = 0.0; breakdown = 0; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cp * cp; idx += blockDim.x) { Dpos[idx] = 0.0; if (Dneg) Dneg[idx] = 0.0; }
+    __syncthreads();
+    if (threadIdx.x < cp) {
+        const int j = threadIdx.x;
+        const double d = Mx[j + j * cp];
+        if (mode == 0) {
+            rs_old[j] = d; rs0[j] = d; active[j] = (j < c && d > 0.0) ? 1 : 0;
+        } else if (mode == 1) {
+            double a = 0.0;
+            if (active[j]) {
+                if (d > 0.0) a = rs_old[j] / d; else atomicExch(&breakdown, 1);
+            }
+            Dpos[j + j * cp] = a;
+            Dneg[j + j * cp] = -a;
+        } else {
+            double b = 0.0, rel = 0.0;
+            if (active[j]) {
+                rel = sqrt(d / rs0[j]);
+                if (rel <= tol) active[j] = 0; else b = d / rs_old[j];
+                rs_old[j] = d;
+                // max over columns (non-negative doubles order like their bit patterns)
+                atomicMax(reinterpret_cast<unsigned long long*>(&maxrel), (unsigned long long)__double_as_longlong(rel));
+            }
+            Dpos[j + j * cp] = b;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && out) { out[0] = maxrel; out[1] = (double)breakdown; }
+}
+
+// M[:, j] = U[:, j] / sqrt(lam_j) for j < ncomp (cp x ncp); flags non-positive eigenvalues
+__global__ void klda_final_kernel(const double* U, const double* lam, int cp, int ncomp, int ncp, double* M,
+                                  int* bad) {
+    if (threadIdx.x == 0) *bad = 0;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cp * ncp; idx += blockDim.x) {
+        const int i = idx % cp, j = idx / cp;
+        double v = 0.0;
+        if (j < ncomp) {
+            if (lam[j] > 0.0) v = U[i + j * cp] / sqrt(lam[j]); else *bad = 1;
+        }
+        M[idx] = v;
+    }
+}
+
+__global__ void symmetrize_kernel(double* S, int cp) {
+    for (int idx = threadIdx.x; idx < cp * cp; idx += blockDim.x) {
+        const int i = idx % cp, j = idx / cp;
+        if (i < j) { const double v = 0.5 * (S[i + j * cp] + S[j + i * cp]); S[i + j * cp] = v; S[j + i * cp] = v; }
+    }
+}
+
+}  // namespace
+
+extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx,
+                               int kernel_id, const double* kparams, const int64_t* y, int nclass,
+                               const double* freq, double alpha_b, double eps_b, double alpha_w,
+                               double eps_w, int ncomp, const fx_solver_opts* opts, double* A,
+                               int64_t lda, double* lambda, fx_model** model, fx_stats* stats) {
+    fx_stats local;
+    fx_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (model) *model = nullptr;
+    if (!ctx) return -1;
+    if (!X) return -2;
+    if (n < 2) return -3;
+    if (d < 1) return -4;
+    if (ldx < n) { fx_set_error("klda_fit: ldx < n (DimensionMismatch)"); return -5; }
+    double kpv[3]; int ipow;
+    if (!kparams || fx_make_kernel_map(kernel_id, kparams, &ipow, kpv)) {
+        fx_set_error("klda_fit: unknown kernel id or invalid kernel parameters");
+        return -6;
+    }
+    if (!y) return -8;
+    const int c = nclass;
+    if (c < 2 || c > 64 || c >= n) { fx_set_error("klda_fit: nclass must lie in 2..64 and be < n"); return -9; }
+    if (!freq) return -10;
+    if (alpha_b != 0.0 || eps_b != 0.0) {
+        fx_set_error("klda_fit: alpha_b / eps_b != 0 is not supported (Sigma_b must stay rank <= c for the "
+                     "reduced c x c eigenproblem)");
+        return alpha_b != 0.0 ? -11 : -12;
+    }
+    if (!(alpha_w >= 0.0 && alpha_w < 1.0)) { fx_set_error("klda_fit: alpha_w must lie in [0,1)"); return -13; }
+    if (eps_w == 0.0 && alpha_w == 0.0) {
+        fx_set_error("klda_fit: Sigma_w = H_w'H_w is singular (rank <= n-c); pass eps_w > 0, eps_w < 0 "
+                     "(relative: |eps_w| tr(Sigma_w)/n) or alpha_w > 0");
+        return FX_ERR_NOT_POSDEF;
+    }
+    if (ncomp < 1 || ncomp > c) { fx_set_error("klda_fit: ncomp must lie in 1..nclass"); return -15; }
+    if (!A) return -17;
+    if (lda < n) { fx_set_error("klda_fit: lda < n (DimensionMismatch)"); return -18; }
+    if (!lambda) return -19;
+    std::vector<double> inv_cnt(c, 0.0), hfreq(freq, freq + c);
+    {
+        std::vector<int64_t> cnt(c, 0);
+        for (int64_t i = 0; i < n; ++i) {
+            if (y[i] < 1 || y[i] > c) { fx_set_error("klda_fit: Index %lld out of range.", (long long)(i + 1)); return -8; }
+            cnt[y[i] - 1]++;                                              // klda.jl:5-12
+        }
+        for (int k = 0; k < c; ++k) {
+            if (cnt[k] == 0) { fx_set_error("klda_fit: class %d is empty", k + 1); return -8; }
+            if (!(freq[k] >= 0.0)) { fx_set_error("klda_fit: negative class frequency"); return -10; }
+            inv_cnt[k] = 1.0 / (double)cnt[k];
+        }
+    }
+
+    FX_CUDA(cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    fx_solver_opts o;
+    fx_resolve_opts(opts, c, &o);
+    const int variant = o.variant;
+    const int G = ctx->world;
+    const int64_t ld = round_up(ceil_div(n, G), 128), n_ld = ld * G, row0 = ld * ctx->rank;
+    int64_t rows_valid = n - row0;
+    if (rows_valid < 0) rows_valid = 0;
+    if (rows_valid > ld) rows_valid = ld;
+    const int64_t d_pad = round_up(d, 16);
+    const int cp = (int)round_up(c, 8), ncp = (int)round_up(ncomp, 8);
+    const int splits = fx_symm_splits(ctx, ld, n_ld);
+    const size_t blk = fx_align256((size_t)cp * ld * 8);
+    const size_t tnscr = fx_ts_tn_scratch(ctx, cp, cp, ld);
+    size_t need = fx_gramstage_bytes(ld, n_ld, d_pad, false) + 12 * blk + fx_align256((size_t)G * cp * ld * 8) +
+                  fx_align256((size_t)splits * cp * ld * 8) + fx_align256(tnscr * 8) + fx_align256((size_t)n_ld * 4) +
+                  fx_align256((size_t)ld * 8) + fx_align256((size_t)ncp * n_ld * 8) + 40 * fx_align256(64 * 64 * 8) + 65536;
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+    cudaStream_t s = ctx->stream;
+    cudaEvent_t e0, e1;
+    FX_CUDA(cudaEventCreate(&e0));
+    FX_CUDA(cudaEventCreate(&e1));
+    FX_CUDA(cudaEventRecord(e0, s));
+    FxTimer tm(ctx);
+
+    GramStage g;
+    g.n = n; g.d = d; g.ld = ld; g.n_ld = n_ld; g.d_pad = d_pad; g.row0 = row0; g.rows_valid = rows_valid;
+    FX_TRY(fx_gramstage_run(ctx, g, X, false, ldx, kernel_id, kpv, false, variant, tm, st));
+
+    auto dalloc = [&](size_t doubles) { return (double*)fx_arena_alloc(ctx, doubles * 8); };
+    double* Eloc = dalloc((size_t)cp * ld);
+    double* KE = dalloc((size_t)cp * ld);
+    double* HbT = dalloc((size_t)cp * ld);
+    double* Gx = dalloc((size_t)cp * ld);
+    double* R = dalloc((size_t)cp * ld);
+    double* P = dalloc((size_t)cp * ld);
+    double* P2 = dalloc((size_t)cp * ld);
+    double* AP = dalloc((size_t)cp * ld);
+    double* T1 = dalloc((size_t)cp * ld);
+    double* Aloc = dalloc((size_t)cp * ld);
+    double* Vg = dalloc((size_t)G * cp * ld);
+    double* Yp = splits > 1 ? dalloc((size_t)splits * cp * ld) : nullptr;
+    double* scr = dalloc(tnscr);
+    double* rowval = dalloc(ld);
+    double* Aout = dalloc((size_t)ncp * n_ld);
+    int* ydev = (int*)fx_arena_alloc(ctx, (size_t)n_ld * 4);
+    double* S1 = dalloc(64 * 64); double* S2 = dalloc(64 * 64); double* Dpos = dalloc(64 * 64);
+    double* Dneg = dalloc(64 * 64); double* U = dalloc(64 * 64); double* Uw = dalloc(64 * 64);
+    double* lam = dalloc(64); double* Mfin = dalloc(64 * 64); double* dfreq = dalloc(64);
+    double* dinv = dalloc(64); double* rs_old = dalloc(64); double* rs0 = dalloc(64);
+    double* dout = dalloc(8);
+    int* active = (int*)fx_arena_alloc(ctx, 64 * 4);
+    int* info = (int*)fx_arena_alloc(ctx, 64);
+    if (!info || !Aout || !Vg) { fx_set_error("internal: arena too small for KLDA"); return FX_ERR_OOM; }
+
+    // labels and class tables
+    {
+        std::vector<int> y32(n_ld, 0);
+        for (int64_t i = 0; i < n; ++i) y32[i] = (int)y[i];
+        FX_CUDA(cudaMemcpyAsync(ydev, y32.data(), (size_t)n_ld * 4, cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaMemcpyAsync(dfreq, hfreq.data(), c * 8, cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaMemcpyAsync(dinv, inv_cnt.data(), c * 8, cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaStreamSynchronize(s));        // y32 goes out of scope
+    }
+    // E (gathered layout, built redundantly from the replicated labels) and the local slice
+    {
+        dim3 grid((unsigned)(n_ld / 128), (unsigned)cp);
+        indicator_kernel<<<grid, 128, 0, s>>>(ydev, n, ld, cp, Vg);
+        ctx->launches++;
+        FX_LAUNCH_CHECK();
+        FX_CUDA(cudaMemcpyAsync(Eloc, Vg + (size_t)ctx->rank * cp * ld, (size_t)cp * ld * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    auto symm = [&](const double* Vsrc, double* Yout) -> int {
+        SymmArgs sa;
+        sa.K = g.K; sa.ldk = n_ld; sa.rows_pad = ld; sa.V = Vsrc; sa.ldr = ld; sa.v_rank_stride = (int64_t)cp * ld;
+        sa.bcols = cp; sa.Y = Yout; sa.Ypart = Yp; sa.splits = splits;
+        tm.begin(&st->symm_ms);
+        int rc = fx_launch_symm(ctx, sa, variant);
+        tm.end();
+        st->symm_launches++;
+        return rc;
+    };
+    auto gather = [&](const double* loc) -> const double* {
+        if (G == 1) return loc;
+        tm.begin(&st->comm_ms);
+        int rc = fxcomm_allgather(ctx->comm, loc, Vg, (size_t)cp * ld, s);
+        tm.end();
+        return rc ? nullptr : Vg;
+    };
+    auto dotmat = [&](const double* Ablk, const double* Bblk, double* out) -> int {   // out = A'B (cp x cp), all-reduced
+        tm.begin(&st->ortho_ms);
+        FX_TRY(fx_launch_ts_tn(ctx, Ablk, cp, Bblk, cp, ld, ld, out, cp, scr, tnscr, variant));
+        tm.end();
+        if (G > 1) {
+            tm.begin(&st->comm_ms);
+            FX_TRY(fxcomm_allreduce_sum(ctx->comm, out, (size_t)cp * cp, s));
+            tm.end();
+        }
+        return 0;
+    };
+
+    // H_b' = rows of sqrt(freq) (class means of K - mu): one K*V pass with the indicators
+    FX_TRY(symm(Vg, KE));                           // Vg currently holds E in gathered layout
+    hb_kernel<<<(unsigned)ceil_div(ld, 256), 256, 0, s>>>(KE, ld, rows_valid, c, cp, dfreq, dinv, HbT);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+
+    // tr(Sigma_w) when the regularisation needs it
+    double trace_w = 0.0;
+    if (eps_w < 0.0 || alpha_w != 0.0) {
+        FX_CUDA(cudaMemsetAsync(rowval, 0, (size_t)ld * 8, s));
+        if (rows_valid > 0) {
+            hw_frob_kernel<<<(unsigned)ceil_div(rows_valid, 8), 256, 0, s>>>(g.K, n_ld, rows_valid, n, KE, ld, c, dinv, rowval);
+            ctx->launches++;
+            FX_LAUNCH_CHECK();
+        }
+        sum_kernel<<<1, 1024, 0, s>>>(rowval, ld, dout + 2);
+        ctx->launches++;
+        FX_LAUNCH_CHECK();
+        if (G > 1) FX_TRY(fxcomm_allreduce_sum(ctx->comm, dout + 2, 1, s));
+        FX_CUDA(cudaMemcpyAsync(ctx->pinned + 200, dout + 2, 8, cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaStreamSynchronize(s));
+        trace_w = ctx->pinned[200] / ((double)(n - c) * (double)(n - c));     // klda.jl:50 scaling, squared
+    }
+    const double eps_abs = eps_w < 0.0 ? -eps_w * trace_w / (double)n : eps_w;
+    const double shift = alpha_w * trace_w / (double)n + eps_abs;            // klda.jl:40-41
+    const double cw = (1.0 - alpha_w) / ((double)(n - c) * (double)(n - c));
+    st->trace = trace_w;
+    if (!(shift > 0.0)) { fx_set_error("klda_fit: regularised Sigma_w is singular"); return FX_ERR_NOT_POSDEF; }
+
+    // AP = cw * K (I - P) K * Pin + shift * Pin
+    auto apply = [&](const double* Pin, double* APout) -> int {
+        const double* v = gather(Pin);
+        if (!v) return FX_ERR_NCCL;
+        FX_TRY(symm(v, T1));
+        FX_TRY(dotmat(Eloc, T1, S1));                                          // class sums  E'T1
+        scale_rows_kernel<<<1, 256, 0, s>>>(S1, dinv, c, cp, S2);              // D^-1 E'T1
+        ctx->launches++;
+        FX_LAUNCH_CHECK();
+        tm.begin(&st->ortho_ms);
+        FX_TRY(fx_launch_ts_nn(ctx, Eloc, cp, S2, cp, cp, -1.0, 1.0, T1, ld, ld, variant));   // T1 -= E D^-1 E'T1
+        tm.end();
+        v = gather(T1);
+        if (!v) return FX_ERR_NCCL;
+        FX_TRY(symm(v, APout));
+        // APout = cw*APout + shift*Pin  ==  scale then axpy
+        FX_TRY(fx_launch_vec_axpy(ctx, (int64_t)cp * ld, cw - 1.0, APout, APout));   // APout *= cw
+        FX_TRY(fx_launch_vec_axpy(ctx, (int64_t)cp * ld, shift, Pin, APout));
+        return 0;
+    };
+
+    // ---- conjugate gradients, all columns in lock-step -----------------------------------------
+    FX_CUDA(cudaMemsetAsync(Gx, 0, (size_t)cp * ld * 8, s));
+    FX_CUDA(cudaMemcpyAsync(R, HbT, (size_t)cp * ld * 8, cudaMemcpyDeviceToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(P, HbT, (size_t)cp * ld * 8, cudaMemcpyDeviceToDevice, s));
+    FX_TRY(dotmat(R, R, S1));
+    cg_scalars_kernel<<<1, 64, 0, s>>>(0, S1, cp, c, rs_old, rs0, active, o.cg_tol, Dpos, Dneg, nullptr);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    int iters = 0;
+    double maxrel = 1.0;
+    bool cg_ok = false;
+    tm.begin(&st->eig_ms);
+    while (iters < o.cg_max_iters) {
+        FX_TRY(apply(P, AP));
+        FX_TRY(dotmat(P, AP, S1));
+        cg_scalars_kernel<<<1, 64, 0, s>>>(1, S1, cp, c, rs_old, rs0, active, o.cg_tol, Dpos, Dneg, dout);
+        ctx->launches++;
+        FX_LAUNCH_CHECK();
+        tm.begin(&st->ortho_ms);
+        FX_TRY(fx_launch_ts_nn(ctx, P, cp, Dpos, cp, cp, 1.0, 1.0, Gx, ld, ld, variant));    // X += P alpha
+        FX_TRY(fx_launch_ts_nn(ctx, AP, cp, Dneg, cp, cp, 1.0, 1.0, R, ld, ld, variant));    // R -= AP alpha
+        tm.end();
+        FX_TRY(dotmat(R, R, S1));
+        cg_scalars_kernel<<<1, 64, 0, s>>>(2, S1, cp, c, rs_old, rs0, active, o.cg_tol, Dpos, nullptr, dout + 4);
+        ctx->launches++;
+        FX_LAUNCH_CHECK();
+        tm.begin(&st->ortho_ms);
+        FX_TRY(fx_launch_ts_nn(ctx, P, cp, Dpos, cp, cp, 1.0, 0.0, P2, ld, ld, variant));    // P2 = P beta
+        tm.end();
+        FX_TRY(fx_launch_vec_axpy(ctx, (int64_t)cp * ld, 1.0, R, P2));                       // P2 += R
+        { double* tmp = P; P = P2; P2 = tmp; }
+        ++iters;
+        FX_CUDA(cudaMemcpyAsync(ctx->pinned + 208, dout, 8 * 8, cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaStreamSynchronize(s));
+        maxrel = ctx->pinned[208 + 4];
+        if (ctx->pinned[208 + 1] != 0.0) {
+            fx_set_error("klda_fit: CG breakdown (p'Ap <= 0): regularised Sigma_w is not positive definite");
+            return FX_ERR_NOT_POSDEF;
+        }
+        if (!(maxrel == maxrel)) { fx_set_error("klda_fit: non-finite CG residual"); return FX_ERR_NOT_CONVERGED; }
+        if (maxrel <= o.cg_tol) { cg_ok = true; break; }
+    }
+    tm.end();
+    st->cg_iters = iters;
+    st->max_residual = maxrel;
+    st->converged = cg_ok ? 1 : 0;
+
+    // ---- reduced c x c eigenproblem S = H_b G, components A = G U / sqrt(lambda) ----------------
+    FX_TRY(dotmat(HbT, Gx, S1));
+    symmetrize_kernel<<<1, 256, 0, s>>>(S1, cp);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    tm.begin(&st->rr_ms);
+    FX_TRY(fx_launch_jacobi(ctx, S1, cp, cp, U, cp, lam, Uw, info));
+    tm.end();
+    klda_final_kernel<<<1, 256, 0, s>>>(U, lam, cp, ncomp, ncp, Mfin, info + 4);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_nn(ctx, Gx, cp, Mfin, cp, ncp, 1.0, 0.0, Aloc, ld, ld, variant));
+    tm.end();
+    if (G > 1) {
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allgather(ctx->comm, Aloc, Vg, (size_t)ncp * ld, s));
+        tm.end();
+        for (int r = 0; r < G; ++r)
+            FX_CUDA(cudaMemcpy2DAsync(Aout + (size_t)r * ld, n_ld * 8, Vg + (size_t)r * ncp * ld, ld * 8, ld * 8, ncp,
+                                      cudaMemcpyDeviceToDevice, s));
+    } else {
+        FX_CUDA(cudaMemcpyAsync(Aout, Aloc, (size_t)ncp * ld * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    tm.begin(&st->d2h_ms);
+    FX_CUDA(cudaMemcpy2DAsync(A, lda * 8, Aout, n_ld * 8, n * 8, ncomp, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(lambda, lam, ncomp * 8, cudaMemcpyDeviceToHost, s));
+    tm.end();
+    st->d2h_bytes += n * ncomp * 8 + ncomp * 8;
+    int hbad[8] = {0};
+    FX_CUDA(cudaMemcpyAsync(hbad, info, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (model) FX_TRY(fx_model_build(ctx, g, kernel_id, kpv, ncomp, Aout, false, true, model));
+    FX_CUDA(cudaEventRecord(e1, s));
+    FX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    st->total_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    tm.resolve();
+    st->block = cp;
+    st->kernel_launches = ctx->launches - launches0;
+    if (hbad[4]) {
+        fx_set_error("klda_fit: a requested generalized eigenvalue is not positive (rank of Sigma_b < ncomp)");
+        if (model && *model) { fx_model_free(*model); *model = nullptr; }
+        return FX_ERR_NOT_POSDEF;
+    }
+    if (!cg_ok) {
+        fx_set_error("klda_fit: CG did not reach relative residual %.1e in %d iterations (got %.3e)", o.cg_tol,
+                     iters, maxrel);
+        return FX_ERR_NOT_CONVERGED;
+    }
+    return 0;
+}

@@ -263,3 +263,56 @@ def test_errors(gpu_ctx):
     with pytest.raises(fxb200.DimensionMismatch):
         fxb200.transform_kpca(X, fxb200.GaussianKernel(1.0), np.zeros((49, 2)), X, ctx=gpu_ctx)
     model.free()
+
+
+# ------------------------------------------------------------------ KLDA (parity unpinned upstream)
+def _klda_case(n, d, c, sep, seed, gamma):
+    X, y0 = mix(n, d, c, sep, seed)
+    y = y0 + 1
+    freq = np.bincount(y0, minlength=c) / n
+    return X, y, freq
+
+
+@pytest.mark.parametrize("n,d,c", [(600, 8, 3), (1500, 32, 5), (900, 16, 10)])
+def test_klda_matches_oracle(gpu_ctx, n, d, c):
+    X, y, freq = _klda_case(n, d, c, 2.0, 71, 1.0 / d)
+    kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+    K = O.kernelmatrix(okern, X)
+    H_b, H_w, _ = O.lda_matrices(K, y, c, freq)
+    _Sb, Sw = O.scatter_matrices(H_b, 0, 0, H_w, 0, 0)
+    eps_w = 1e-6 * np.trace(Sw) / n
+    Ao, Lo = O.klda(X, okern, y, c, freq, eps_w=eps_w)
+    A, L, model, st = fxb200.klda(X, kern, y, c, freq, eps_w=eps_w, ctx=gpu_ctx, return_model=True,
+                                  return_stats=True)
+    assert st["converged"] == 1 and st["cg_iters"] > 0
+    np.testing.assert_allclose(L, Lo, rtol=1e-7)
+    # vectors: compare the spanned subspace (clustered eigenvalues) and the B-normalisation
+    assert sin_angle(A, Ao) < 1e-5
+    Swr = Sw + eps_w * np.eye(n)
+    np.testing.assert_allclose(np.diag(A.T @ Swr @ A), 1.0, rtol=1e-6)
+    # relative eps_w (negative) resolves to the same problem
+    A2, L2 = fxb200.klda(X, kern, y, c, freq, eps_w=-1e-6, ctx=gpu_ctx)
+    np.testing.assert_allclose(L2, Lo, rtol=1e-6)
+    # transform_klda = k(Z,X) A, no centring (klda.jl:71)
+    Z, _ = mix(77, d, c, 2.0, 72)
+    T = model.transform(Z)
+    To = O.transform_klda(X, okern, A, Z)
+    relclose(T, To, 1e-10)
+    relclose(fxb200.transform_klda(X, kern, A, Z, ctx=gpu_ctx), To, 1e-10)
+    model.free()
+
+
+def test_klda_alpha_w_and_errors(gpu_ctx):
+    n, d, c = 500, 6, 4
+    X, y, freq = _klda_case(n, d, c, 2.0, 73, 1.0 / d)
+    kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+    Ao, Lo = O.klda(X, okern, y, c, freq, alpha_w=0.05)
+    A, L = fxb200.klda(X, kern, y, c, freq, alpha_w=0.05, ctx=gpu_ctx)
+    np.testing.assert_allclose(L, Lo, rtol=1e-7)
+    ybad = y.copy(); ybad[3] = c + 1
+    with pytest.raises(ValueError):                     # klda.jl:8 "Index out of range"
+        fxb200.klda(X, kern, ybad, c, freq, eps_w=1e-3, ctx=gpu_ctx)
+    with pytest.raises(fxb200.FxError):                 # Sigma_w singular without regularisation
+        fxb200.klda(X, kern, y, c, freq, ctx=gpu_ctx)
+    with pytest.raises(fxb200.DimensionMismatch):       # klda.jl:16
+        fxb200.klda(X, kern, y[:-1], c, freq, eps_w=1e-3, ctx=gpu_ctx)
