@@ -26,7 +26,7 @@ void fx_resolve_opts(const fx_solver_opts* in, int k, fx_solver_opts* out) {
     if (o.max_steps <= 0) o.max_steps = 300;
     if (!(o.tol > 0.0)) o.tol = 1e-12;
     if (o.seed == 0) o.seed = 0x5eedULL;
-    if (o.cg_max_iters <= 0) o.cg_max_iters = 2000;
+    if (o.cg_max_iters <= 0) o.cg_max_iters = 4000;
     if (!(o.cg_tol > 0.0)) o.cg_tol = 1e-10;
     *out = o;
 }

@@ -60,7 +60,7 @@ typedef struct fx_solver_opts {
     int32_t variant;      /* 0 = tuned kernels, 1 = naive CUDA kernels (debug cross-check)   */
     double  tol;          /* Ritz residual tolerance relative to |theta_1| (default 1e-12)   */
     uint64_t seed;        /* start-block seed (default 0x5eed)                               */
-    int32_t cg_max_iters; /* KLDA: CG iterations allowed (default 2000)                      */
+    int32_t cg_max_iters; /* KLDA: CG iterations allowed (default 4000)                      */
     int32_t reserved;
     double  cg_tol;       /* KLDA: CG relative residual (default 1e-10)                      */
 } fx_solver_opts;

@@ -273,14 +273,15 @@ def _klda_case(n, d, c, sep, seed, gamma):
     return X, y, freq
 
 
-@pytest.mark.parametrize("n,d,c", [(600, 8, 3), (1500, 32, 5), (900, 16, 10)])
-def test_klda_matches_oracle(gpu_ctx, n, d, c):
+@pytest.mark.parametrize("n,d,c,rel", [(600, 8, 3, 1e-3), (1500, 32, 5, 1e-6), (900, 16, 10, 1e-6),
+                                       (2000, 64, 10, 1e-6)])
+def test_klda_matches_oracle(gpu_ctx, n, d, c, rel):
     X, y, freq = _klda_case(n, d, c, 2.0, 71, 1.0 / d)
     kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
     K = O.kernelmatrix(okern, X)
     H_b, H_w, _ = O.lda_matrices(K, y, c, freq)
     _Sb, Sw = O.scatter_matrices(H_b, 0, 0, H_w, 0, 0)
-    eps_w = 1e-6 * np.trace(Sw) / n
+    eps_w = rel * np.trace(Sw) / n
     Ao, Lo = O.klda(X, okern, y, c, freq, eps_w=eps_w)
     A, L, model, st = fxb200.klda(X, kern, y, c, freq, eps_w=eps_w, ctx=gpu_ctx, return_model=True,
                                   return_stats=True)
@@ -291,7 +292,7 @@ def test_klda_matches_oracle(gpu_ctx, n, d, c):
     Swr = Sw + eps_w * np.eye(n)
     np.testing.assert_allclose(np.diag(A.T @ Swr @ A), 1.0, rtol=1e-6)
     # relative eps_w (negative) resolves to the same problem
-    A2, L2 = fxb200.klda(X, kern, y, c, freq, eps_w=-1e-6, ctx=gpu_ctx)
+    A2, L2 = fxb200.klda(X, kern, y, c, freq, eps_w=-rel, ctx=gpu_ctx)
     np.testing.assert_allclose(L2, Lo, rtol=1e-6)
     # transform_klda = k(Z,X) A, no centring (klda.jl:71)
     Z, _ = mix(77, d, c, 2.0, 72)
@@ -316,3 +317,8 @@ def test_klda_alpha_w_and_errors(gpu_ctx):
         fxb200.klda(X, kern, y, c, freq, ctx=gpu_ctx)
     with pytest.raises(fxb200.DimensionMismatch):       # klda.jl:16
         fxb200.klda(X, kern, y[:-1], c, freq, eps_w=1e-3, ctx=gpu_ctx)
+    # an ill-conditioned pencil that CG cannot finish in the allowed iterations reports
+    # "not converged" (the analogue of LAPACKException, common.jl:90-92) instead of a wrong answer
+    with pytest.raises(fxb200.FxError) as ei:
+        fxb200.klda(X, kern, y, c, freq, eps_w=-1e-9, ctx=gpu_ctx, opts=fxb200.make_opts(cg_max_iters=20))
+    assert ei.value.code == 4
