@@ -245,19 +245,19 @@ def run_ours(args):
             ms = float(t.item())
         return ms, acc, launches
 
-    for _ in range(args.warmup):
-        fit_dev()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                       # nvidia-smi needs ~1 s to start: launch before warm-up
+    for _ in range(args.warmup):
+        fit_dev()
     ms_dev, acc, launches = timed(fit_dev, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     maxres, conv, block, trace = st.max_residual, st.converged, st.block, st.trace
     lam_dev = Ld.cpu().numpy().copy()
 
     for _ in range(max(1, min(args.warmup, 2))):
         fit_host()
-    ms_e2e, acc_h, _ = timed(fit_host, args.steps)
+    ms_e2e, acc_h, launches_h = timed(fit_host, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
     h2d, d2h = st.h2d_bytes, st.d2h_bytes
     lam_host = Lh.numpy().copy()
 
@@ -286,6 +286,14 @@ def run_ours(args):
         symm_ms = acc["symm_ms"] / max(1, acc["symm_launches"])
         gram_flops = 2.0 * ld * n * d                        # per rank, per launch
         gram_tf = gram_flops / gram_ms / 1e9
+        traffic = None                                       # DRAM bytes per Gram launch from the committed
+        try:                                                 # ncu --set full capture of the same shape
+            tj = json.load(open(os.path.join(ROOT, "profiles", "gram_traffic.json")))
+            key = "n%d_d%d_rows%d" % (n, d, ld)
+            if key in tj:
+                traffic = tj[key]
+        except Exception:
+            pass
         line = {
             "metric": "kpca_fit_seconds", "value": ms_dev / K / 1e3, "unit": "s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": ms_dev / K, "higher_is_better": False,
@@ -293,11 +301,11 @@ def run_ours(args):
             "config": workload_config(cfg, world),
             "e2e": {"value": ms_e2e / K / 1e3, "unit": "s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "api": "fx_kpca_fit_f64 (host pinned X in, V/lambda out)"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches + launches_h),
             "gram_tflops": gram_tf * world,
             "roofline": {"bound": "tensor", "kernel": "gram_dmma_kernel", "achieved": gram_tf,
                          "peak": peak_dmma, "unit": "TFLOP/s", "frac": gram_tf / peak_dmma,
-                         "traffic": None,
+                         "traffic": traffic,
                          "peak_source": "fp64 DMMA.8x8x4 issue-rate microbenchmark measured live in this run "
                                         "(fx_bench_kernel 4); MEASURED_PEAKS.json has no fp64 entry",
                          "algorithmic": "2*rows_per_rank*n*d flops per launch = %.4g" % gram_flops},
