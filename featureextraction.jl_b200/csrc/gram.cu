@@ -30,9 +30,24 @@ struct GramParams {
     double* rowpart; long rows_pad;
     long rows_valid, cols_valid, diag_shift;
     int kt;
-    int tiles_x; long tiles_total;
+    int tiles_x, tiles_y; long tiles_total;
     KernelMap km;
 };
+
+// Tile order: column panels of PANEL tile-columns swept over all row blocks, so that the panel's
+// slab of the column operand (PANEL x 131 KB at d=256) stays L2-resident while the row operand
+// streams; a plain row-major sweep re-reads all of X from HBM once per row block.
+constexpr int PANEL = 128;
+__device__ __forceinline__ void tile_coords(const GramParams& p, long tile, long& i0, long& j0, int& tx) {
+    const long per_panel = (long)PANEL * p.tiles_y;
+    const int panel = (int)(tile / per_panel);
+    const long within = tile - (long)panel * per_panel;
+    const int pw = min(PANEL, p.tiles_x - panel * PANEL);      // last panel may be narrower
+    const int ty = (int)(within / pw);
+    tx = panel * PANEL + (int)(within - (long)ty * pw);
+    i0 = (long)ty * BM;
+    j0 = (long)tx * BN;
+}
 
 __device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -100,7 +115,8 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         if (warp != 4) return;
         int it = 0;
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
-            const long i0 = (tile / p.tiles_x) * BM, j0 = (tile % p.tiles_x) * BN;
+            long i0, j0; int tx;
+            tile_coords(p, tile, i0, j0, tx);
             for (int kt = 0; kt < KT; ++kt, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);    // passes at once on first use
@@ -123,7 +139,8 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     const int wm = warp >> 1, wn = warp & 1;
     int it = 0, tcount = 0;
     for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tcount) {
-        const long i0 = (tile / p.tiles_x) * BM, j0 = (tile % p.tiles_x) * BN;
+        long i0, j0; int tx;
+        tile_coords(p, tile, i0, j0, tx);
         double acc[8][4][2];
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt)
@@ -173,7 +190,7 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         else      gram_epilogue<KID, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
         if (p.rowpart) {
             bar_sync_compute();                  // both column halves of every row are in smem
-            p.rowpart[(tile % p.tiles_x) * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
+            p.rowpart[(long)tx * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
         }
     }
 }
@@ -238,6 +255,7 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     p.rows_valid = a.rows_valid; p.cols_valid = a.cols_valid; p.diag_shift = a.diag_shift;
     p.kt = (int)(a.d_pad / BK);
     p.tiles_x = (int)(a.ldk / BN);
+    p.tiles_y = (int)(a.rows_pad / BM);
     p.tiles_total = (long)(a.ldk / BN) * (a.rows_pad / BM);
     p.km.id = a.kernel_id; p.km.p0 = a.kp[0]; p.km.p1 = a.kp[1]; p.km.p2 = a.kp[2];
     double tmp[3];

@@ -9,8 +9,8 @@
 
 namespace {
 
-constexpr int JT = 1024;                         // threads of the Jacobi CTA
-constexpr int J_SMEM_MAX_M = 160;                // A kept in shared memory up to this order
+constexpr int J_SMEM_BOTH_MAX_M = 112;           // A and V both in shared memory up to this order
+constexpr int J_SMEM_MAX_M = 160;                // A alone in shared memory up to this order
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
     v = warp_sum(v);
@@ -33,51 +33,56 @@ __device__ __forceinline__ void rr_pair(int rnd, int i, int mp, int& p, int& q) 
         p = mp - 1;
         q = rnd;
     } else {
-        p = (rnd + i) % (mp - 1);
-        q = (rnd - i + (mp - 1)) % (mp - 1);
+        p = rnd + i;
+        if (p >= mp - 1) p -= mp - 1;
+        q = rnd - i;
+        if (q < 0) q += mp - 1;
     }
     if (p > q) { const int x = p; p = q; q = x; }
 }
 
-// A (m x m, lda) symmetric, destroyed.  V (m x m, ldv) receives the eigenvectors (unsorted),
-// then w / Vout the sorted (descending) results.
-__global__ void __launch_bounds__(JT, 1) jacobi_kernel(double* Ag, int lda_g, int m, double* V, int ldv,
-                                                       double* w, double* Vout, int ldvo, int* info,
-                                                       int use_smem, int max_sweeps) {
+// A (m x m, lda) symmetric, destroyed.  Vg (m x m, ldv) is global scratch for the accumulated
+// rotations when they do not fit in shared memory; w / Vout receive the sorted (descending)
+// eigenvalues / eigenvectors.  One warp per rotation pair, lanes over rows / columns.
+__global__ void __launch_bounds__(1024, 1) jacobi_kernel(double* Ag, int lda_g, int m, double* Vg, int ldvg,
+                                                         double* w, double* Vout, int ldvo, int* info,
+                                                         int smem_mode, int max_sweeps) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[33];
     __shared__ double rot_c[512], rot_s[512];
     __shared__ int rot_p[512], rot_q[512];
     __shared__ int s_rank[1024];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int mp = m + (m & 1);
     const int half = mp / 2;
 
     double* A = Ag;
-    int lda = lda_g;
-    if (use_smem) {
+    double* V = Vg;
+    int lda = lda_g, ldv = ldvg;
+    if (smem_mode >= 1) {
         lda = m | 1;                              // odd stride: conflict-free row access
         A = sm;
-        for (int idx = tid; idx < m * m; idx += JT) {
-            const int i = idx % m, j = idx / m;
-            A[i + j * lda] = Ag[i + (long)j * lda_g];
-        }
+        for (int j = warp; j < m; j += nwarps)
+            for (int i = lane; i < m; i += 32) A[i + j * lda] = Ag[i + (long)j * lda_g];
     }
-    for (int idx = tid; idx < m * m; idx += JT) {
-        const int i = idx % m, j = idx / m;
-        V[i + (long)j * ldv] = (i == j) ? 1.0 : 0.0;
+    if (smem_mode >= 2) {
+        ldv = m | 1;
+        V = sm + (size_t)m * lda;
     }
+    for (int j = warp; j < m; j += nwarps)
+        for (int i = lane; i < m; i += 32) V[i + (long)j * ldv] = (i == j) ? 1.0 : 0.0;
     __syncthreads();
 
     int sweeps = 0, converged = 0;
     double prev_off = 0.0;
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         double off = 0.0, dg = 0.0;
-        for (int idx = tid; idx < m * m; idx += JT) {
-            const int i = idx % m, j = idx / m;
-            const double a = A[i + j * lda];
-            if (i == j) dg += a * a; else off += a * a;
-        }
+        for (int j = warp; j < m; j += nwarps)
+            for (int i = lane; i < m; i += 32) {
+                const double a = A[i + (long)j * lda];
+                if (i == j) dg += a * a; else off += a * a;
+            }
         off = block_sum(off, red);
         dg = block_sum(dg, red);
         if (off <= 1e-30 * dg || off == 0.0) { converged = 1; break; }
@@ -87,16 +92,16 @@ __global__ void __launch_bounds__(JT, 1) jacobi_kernel(double* Ag, int lda_g, in
         sweeps++;
         for (int rnd = 0; rnd < mp - 1; ++rnd) {
             // phase 1: rotation parameters for the pairs of this round
-            for (int i = tid; i < half; i += JT) {
+            for (int i = tid; i < half; i += nt) {
                 int pp, qq;
                 rr_pair(rnd, i, mp, pp, qq);
                 double c = 1.0, s = 0.0;
                 if (qq < m) {
-                    const double apq = A[pp + qq * lda];
+                    const double apq = A[pp + (long)qq * lda];
                     if (fabs(apq) > 1e-300) {
-                        const double tau = (A[qq + qq * lda] - A[pp + pp * lda]) / (2.0 * apq);
+                        const double tau = (A[qq + (long)qq * lda] - A[pp + (long)pp * lda]) / (2.0 * apq);
                         const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + tt * tt);
+                        c = rsqrt(1.0 + tt * tt);
                         s = tt * c;
                     }
                 } else {
@@ -105,53 +110,54 @@ __global__ void __launch_bounds__(JT, 1) jacobi_kernel(double* Ag, int lda_g, in
                 rot_p[i] = pp; rot_q[i] = qq; rot_c[i] = c; rot_s[i] = s;
             }
             __syncthreads();
-            // phase 2: column rotations  A <- A J,  V <- V J
-            for (int idx = tid; idx < half * m; idx += JT) {
-                const int pr = idx / m, r = idx - pr * m;
+            // phase 2: column rotations  A <- A J,  V <- V J   (warp per pair, lanes over rows)
+            for (int pr = warp; pr < half; pr += nwarps) {
                 const int pp = rot_p[pr], qq = rot_q[pr];
-                if (qq < 0) continue;
                 const double c = rot_c[pr], s = rot_s[pr];
-                if (s == 0.0) continue;
-                const double ap = A[r + pp * lda], aq = A[r + qq * lda];
-                A[r + pp * lda] = c * ap - s * aq;
-                A[r + qq * lda] = s * ap + c * aq;
-                const double vp = V[r + (long)pp * ldv], vq = V[r + (long)qq * ldv];
-                V[r + (long)pp * ldv] = c * vp - s * vq;
-                V[r + (long)qq * ldv] = s * vp + c * vq;
+                if (qq < 0 || s == 0.0) continue;
+                double* Ap = A + (long)pp * lda; double* Aq = A + (long)qq * lda;
+                double* Vp = V + (long)pp * ldv; double* Vq = V + (long)qq * ldv;
+                for (int r = lane; r < m; r += 32) {
+                    const double ap = Ap[r], aq = Aq[r], vp = Vp[r], vq = Vq[r];
+                    Ap[r] = c * ap - s * aq;
+                    Aq[r] = s * ap + c * aq;
+                    Vp[r] = c * vp - s * vq;
+                    Vq[r] = s * vp + c * vq;
+                }
             }
             __syncthreads();
-            // phase 3: row rotations  A <- J' A
-            for (int idx = tid; idx < half * m; idx += JT) {
-                const int pr = idx / m, cc = idx - pr * m;
+            // phase 3: row rotations  A <- J' A   (warp per pair, lanes over columns)
+            for (int pr = warp; pr < half; pr += nwarps) {
                 const int pp = rot_p[pr], qq = rot_q[pr];
-                if (qq < 0) continue;
                 const double c = rot_c[pr], s = rot_s[pr];
-                if (s == 0.0) continue;
-                const double ap = A[pp + cc * lda], aq = A[qq + cc * lda];
-                double np_ = c * ap - s * aq, nq_ = s * ap + c * aq;
-                if (cc == qq) np_ = 0.0;          // the annihilated pair, exactly
-                if (cc == pp) nq_ = 0.0;
-                A[pp + cc * lda] = np_;
-                A[qq + cc * lda] = nq_;
+                if (qq < 0 || s == 0.0) continue;
+                for (int cc = lane; cc < m; cc += 32) {
+                    const double ap = A[pp + (long)cc * lda], aq = A[qq + (long)cc * lda];
+                    double np_ = c * ap - s * aq, nq_ = s * ap + c * aq;
+                    if (cc == qq) np_ = 0.0;      // the annihilated pair, exactly
+                    if (cc == pp) nq_ = 0.0;
+                    A[pp + (long)cc * lda] = np_;
+                    A[qq + (long)cc * lda] = nq_;
+                }
             }
             __syncthreads();
         }
     }
     // sort descending by rank counting (stable), scatter eigenvectors
-    for (int i = tid; i < m; i += JT) {
-        const double di = A[i + i * lda];
+    for (int i = tid; i < m; i += nt) {
+        const double di = A[i + (long)i * lda];
         int rank = 0;
         for (int j = 0; j < m; ++j) {
-            const double dj = A[j + j * lda];
+            const double dj = A[j + (long)j * lda];
             rank += (dj > di) || (dj == di && j < i);
         }
         w[rank] = di;
         s_rank[i] = rank;
     }
     __syncthreads();
-    for (int idx = tid; idx < m * m; idx += JT) {
-        const int r = idx % m, i = idx / m;
-        Vout[r + (long)s_rank[i] * ldvo] = V[r + (long)i * ldv];
+    for (int j = warp; j < m; j += nwarps) {
+        const int dst = s_rank[j];
+        for (int r = lane; r < m; r += 32) Vout[r + (long)dst * ldvo] = V[r + (long)j * ldv];
     }
     if (tid == 0 && info) { info[0] = sweeps; info[1] = converged; }
 }
@@ -275,14 +281,18 @@ int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int l
         fx_set_error("jacobi: order %d out of range", m);
         return FX_ERR_CUDA;
     }
-    const int use_smem = (m <= J_SMEM_MAX_M) ? 1 : 0;
-    const size_t smem = use_smem ? (size_t)m * (m | 1) * 8 : 0;
+    const int mode = (m <= J_SMEM_BOTH_MAX_M) ? 2 : ((m <= J_SMEM_MAX_M) ? 1 : 0);
+    const size_t smem = (size_t)mode * m * (m | 1) * 8;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         FX_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    jacobi_kernel<<<1, JT, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, use_smem, 40);
+    // one warp per rotation pair; small problems use a small CTA (cheaper barriers)
+    int threads = 32 * ((m + 1) / 2);
+    if (threads < 64) threads = 64;
+    if (threads > 1024) threads = 1024;
+    jacobi_kernel<<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, mode, 40);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;

@@ -92,13 +92,16 @@ __global__ void __launch_bounds__(256, 1) ts_tn_kernel(const TnParams p) {
     }
 }
 
+// one warp per output element, lanes stride over the chunk partials (fixed order: deterministic)
 __global__ void ts_tn_reduce_kernel(const double* __restrict__ part, int nchunks, int ma, int nb,
                                     double* __restrict__ H, int ldh) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (idx >= ma * nb) return;
     double s = 0.0;
-    for (int c = 0; c < nchunks; ++c) s += part[(long)c * ma * nb + idx];
-    H[(long)(idx / ma) * ldh + (idx % ma)] = s;
+    for (int c = lane; c < nchunks; c += 32) s += part[(long)c * ma * nb + idx];
+    s = warp_sum(s);
+    if (lane == 0) H[(long)(idx / ma) * ldh + (idx % ma)] = s;
 }
 
 __global__ void ts_tn_naive_kernel(const double* A, const double* B, long ld, long rows, int ma, int nb,
@@ -235,7 +238,7 @@ int fx_launch_ts_tn(fx_ctx* ctx, const double* A, int ma, const double* B, int n
     ts_tn_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     ctx->launches++;
     FX_LAUNCH_CHECK();
-    ts_tn_reduce_kernel<<<(unsigned)ceil_div((int64_t)ma * nb, 256), 256, 0, ctx->stream>>>(scratch, p.nchunks, ma, nb, H, ldh);
+    ts_tn_reduce_kernel<<<(unsigned)ceil_div((int64_t)ma * nb, 8), 256, 0, ctx->stream>>>(scratch, p.nchunks, ma, nb, H, ldh);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;
