@@ -41,35 +41,46 @@ __device__ __forceinline__ void rr_pair(int rnd, int i, int mp, int& p, int& q) 
     if (p > q) { const int x = p; p = q; q = x; }
 }
 
+// Symmetric Schur rotation annihilating a_pq:  t = h sgn(d) / (|d| + sqrt(d^2 + h^2)) with
+// d = a_qq - a_pp, h = 2 a_pq; c = 1/sqrt(1+t^2), s = t c.  rsqrt/rcp based (no IEEE div/sqrt).
+__device__ __forceinline__ void schur_rotation(double app, double aqq, double apq, double& c, double& s) {
+    c = 1.0; s = 0.0;
+    if (fabs(apq) > 1e-300) {
+        const double d = aqq - app, h = 2.0 * apq;
+        const double r2 = fma(d, d, h * h);
+        const double sq = r2 * rsqrt(r2);
+        const double den = fabs(d) + sq;
+        const double t = (d >= 0.0 ? h : -h) * __drcp_rn(den);
+        c = rsqrt(fma(t, t, 1.0));
+        s = t * c;
+    }
+}
+
 // A (m x m, lda) symmetric, destroyed.  Vg (m x m, ldv) is global scratch for the accumulated
 // rotations when they do not fit in shared memory; w / Vout receive the sorted (descending)
-// eigenvalues / eigenvectors.  One warp per rotation pair, lanes over rows / columns.
+// eigenvalues / eigenvectors.  One warp owns a rotation pair for the whole round: it derives the
+// rotation itself, rotates its two columns of A and V, and after one barrier its two rows of A.
+template <bool SMEM_A, bool SMEM_V>
 __global__ void __launch_bounds__(1024, 1) jacobi_kernel(double* Ag, int lda_g, int m, double* Vg, int ldvg,
                                                          double* w, double* Vout, int ldvo, int* info,
-                                                         int smem_mode, int max_sweeps) {
+                                                         int max_sweeps) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[33];
-    __shared__ double rot_c[512], rot_s[512];
-    __shared__ int rot_p[512], rot_q[512];
     __shared__ int s_rank[1024];
+    __shared__ double rot_c[512], rot_s[512];     // written and read by the pair's owner warp only
+    __shared__ int rot_p[512], rot_q[512];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int mp = m + (m & 1);
     const int half = mp / 2;
 
-    double* A = Ag;
-    double* V = Vg;
-    int lda = lda_g, ldv = ldvg;
-    if (smem_mode >= 1) {
-        lda = m | 1;                              // odd stride: conflict-free row access
-        A = sm;
+    const int lda = SMEM_A ? (m | 1) : lda_g;     // odd stride in smem: conflict-free row access
+    const int ldv = SMEM_V ? (m | 1) : ldvg;
+    double* A = SMEM_A ? sm : Ag;
+    double* V = SMEM_V ? (sm + (size_t)m * (m | 1)) : Vg;
+    if (SMEM_A)
         for (int j = warp; j < m; j += nwarps)
             for (int i = lane; i < m; i += 32) A[i + j * lda] = Ag[i + (long)j * lda_g];
-    }
-    if (smem_mode >= 2) {
-        ldv = m | 1;
-        V = sm + (size_t)m * lda;
-    }
     for (int j = warp; j < m; j += nwarps)
         for (int i = lane; i < m; i += 32) V[i + (long)j * ldv] = (i == j) ? 1.0 : 0.0;
     __syncthreads();
@@ -85,35 +96,24 @@ __global__ void __launch_bounds__(1024, 1) jacobi_kernel(double* Ag, int lda_g, 
             }
         off = block_sum(off, red);
         dg = block_sum(dg, red);
-        if (off <= 1e-30 * dg || off == 0.0) { converged = 1; break; }
+        if (off <= 1e-28 * dg || off == 0.0) { converged = 1; break; }   // off_F <= 1e-14 |A|_F
         // rounding floor reached: the off-diagonal norm stopped contracting
         if (sweep > 2 && off > 0.25 * prev_off && off <= 1e-24 * dg) { converged = 1; break; }
         prev_off = off;
         sweeps++;
         for (int rnd = 0; rnd < mp - 1; ++rnd) {
-            // phase 1: rotation parameters for the pairs of this round
-            for (int i = tid; i < half; i += nt) {
+            // phase A: rotation + column rotations  A <- A J,  V <- V J   (lanes over rows)
+            for (int pr = warp; pr < half; pr += nwarps) {
                 int pp, qq;
-                rr_pair(rnd, i, mp, pp, qq);
+                rr_pair(rnd, pr, mp, pp, qq);
                 double c = 1.0, s = 0.0;
                 if (qq < m) {
-                    const double apq = A[pp + (long)qq * lda];
-                    if (fabs(apq) > 1e-300) {
-                        const double tau = (A[qq + (long)qq * lda] - A[pp + (long)pp * lda]) / (2.0 * apq);
-                        const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = rsqrt(1.0 + tt * tt);
-                        s = tt * c;
-                    }
+                    schur_rotation(A[pp + (long)pp * lda], A[qq + (long)qq * lda], A[pp + (long)qq * lda], c, s);
                 } else {
                     qq = -1;
                 }
-                rot_p[i] = pp; rot_q[i] = qq; rot_c[i] = c; rot_s[i] = s;
-            }
-            __syncthreads();
-            // phase 2: column rotations  A <- A J,  V <- V J   (warp per pair, lanes over rows)
-            for (int pr = warp; pr < half; pr += nwarps) {
-                const int pp = rot_p[pr], qq = rot_q[pr];
-                const double c = rot_c[pr], s = rot_s[pr];
+                __syncwarp();                     // all lanes have read the 2x2 block before it changes
+                if (lane == 0) { rot_c[pr] = c; rot_s[pr] = s; rot_p[pr] = pp; rot_q[pr] = qq; }
                 if (qq < 0 || s == 0.0) continue;
                 double* Ap = A + (long)pp * lda; double* Aq = A + (long)qq * lda;
                 double* Vp = V + (long)pp * ldv; double* Vq = V + (long)qq * ldv;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(1024, 1) jacobi_kernel(double* Ag, int lda_g, 
                 }
             }
             __syncthreads();
-            // phase 3: row rotations  A <- J' A   (warp per pair, lanes over columns)
+            // phase B: row rotations  A <- J' A   (same warp, same pairs; lanes over columns)
             for (int pr = warp; pr < half; pr += nwarps) {
                 const int pp = rot_p[pr], qq = rot_q[pr];
                 const double c = rot_c[pr], s = rot_s[pr];
@@ -283,16 +283,21 @@ int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int l
     }
     const int mode = (m <= J_SMEM_BOTH_MAX_M) ? 2 : ((m <= J_SMEM_MAX_M) ? 1 : 0);
     const size_t smem = (size_t)mode * m * (m | 1) * 8;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        FX_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    // balanced: every warp owns the same number of rotation pairs (at most 16)
+    const int half = (m + 1) / 2;
+    int per = (half + 31) / 32;
+    int nwarps = (half + per - 1) / per;
+    if (nwarps < 2) nwarps = 2;
+    const int threads = 32 * nwarps;
+    static size_t smem_set[3] = {0, 0, 0};
+    if (smem > smem_set[mode]) {
+        if (mode == 2) FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (mode == 1) FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[mode] = smem;
     }
-    // one warp per rotation pair; small problems use a small CTA (cheaper barriers)
-    int threads = 32 * ((m + 1) / 2);
-    if (threads < 64) threads = 64;
-    if (threads > 1024) threads = 1024;
-    jacobi_kernel<<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, mode, 40);
+    if (mode == 2) jacobi_kernel<true, true><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40);
+    else if (mode == 1) jacobi_kernel<true, false><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40);
+    else jacobi_kernel<false, false><<<1, threads, 0, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;

@@ -22,7 +22,7 @@ void fx_resolve_opts(const fx_solver_opts* in, int k, fx_solver_opts* out) {
     if (o.block < kb) o.block = kb;
     o.block = (int)round_up(o.block, 8);
     if (o.block > 64) o.block = 64;
-    if (o.max_blocks <= 1) o.max_blocks = 5;
+    if (o.max_blocks <= 1) o.max_blocks = 3;
     if (o.max_steps <= 0) o.max_steps = 300;
     if (!(o.tol > 0.0)) o.tol = 1e-12;
     if (o.seed == 0) o.seed = 0x5eedULL;

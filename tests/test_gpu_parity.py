@@ -184,7 +184,7 @@ def test_kpca_slow_decay_restarts(gpu_ctx):
     X = rng.standard_normal((1400, 16))
     kern, okern = fxb200.GaussianKernel(1 / 16), O.GaussianKernel(1 / 16)
     V, L, st = fxb200.kpca(X, kern, k=6, ctx=gpu_ctx, return_stats=True,
-                           opts=fxb200.make_opts(max_blocks=3))
+                           opts=fxb200.make_opts(max_blocks=2))
     Vo, Lo = O.kpca(X, okern)
     np.testing.assert_allclose(L, Lo[:6], rtol=1e-10)
     assert st["restarts"] >= 1 and st["converged"] == 1
