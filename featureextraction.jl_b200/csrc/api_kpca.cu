@@ -175,6 +175,12 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     fx_resolve_opts(opts, k, &o);
     const int G = ctx->world;
     const int64_t ld = round_up(ceil_div(n, G), 128), n_ld = ld * G;
+    if (!opts || opts->max_blocks <= 1) {
+        // basis depth: a deeper basis saves K*V passes but makes every Rayleigh-Ritz (device
+        // Jacobi, ~m^3) dearer; keep 5 blocks while a pass over this rank's K costs > 2 ms
+        const double pass_ms = 8.0 * (double)ld * (double)n_ld / 6.5e9;
+        o.max_blocks = pass_ms > 2.0 ? 5 : 3;
+    }
     const int64_t row0 = ld * ctx->rank;
     int64_t rows_valid = n - row0;
     if (rows_valid < 0) rows_valid = 0;
