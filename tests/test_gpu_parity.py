@@ -322,3 +322,75 @@ def test_klda_alpha_w_and_errors(gpu_ctx):
     with pytest.raises(fxb200.FxError) as ei:
         fxb200.klda(X, kern, y, c, freq, eps_w=-1e-9, ctx=gpu_ctx, opts=fxb200.make_opts(cg_max_iters=20))
     assert ei.value.code == 4
+
+
+# ------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("n,d,k", [(300, 1, 1), (257, 3, 1), (1025, 1000, 3), (640, 17, 64), (129, 5, 129)])
+def test_kpca_shapes(gpu_ctx, n, d, k):
+    """k = 1, d = 1, d not a multiple of 16, block width 64, n just above the dense threshold,
+    and the all-components request of the reference (k = n, dense path)."""
+    X, _ = mix(n, d, 4, 3.0, 81)
+    gamma = 1.0 / d
+    kern, okern = fxb200.GaussianKernel(gamma), O.GaussianKernel(gamma)
+    V, L, st = fxb200.kpca(X, kern, k=k, ctx=gpu_ctx, return_stats=True)
+    Vo, Lo = O.kpca(X, okern)
+    scale = Lo[0]
+    assert np.abs(L - Lo[:k]).max() <= 1e-10 * scale
+    assert np.abs(V.T @ V - np.eye(k)).max() < 1e-10
+    kk = min(k, 3)                      # leading, well separated part
+    assert sin_angle(V[:, :kk], Vo[:, :kk]) < 1e-7
+    assert st["dense_path"] == (1 if (n <= 256 or k > 64) else 0)
+
+
+def test_kpca_degenerate_inputs(gpu_ctx):
+    """Duplicate observations (rank-deficient K) and constant data (K~ = 0): eigenvalues must
+    match the dense reference path; any orthonormal basis is acceptable for a zero spectrum."""
+    rng = np.random.default_rng(82)
+    base = rng.standard_normal((50, 6))
+    X = np.repeat(base, 8, axis=0)                      # 400 rows, 50 distinct
+    kern, okern = fxb200.GaussianKernel(0.2), O.GaussianKernel(0.2)
+    V, L = fxb200.kpca(X, kern, k=5, ctx=gpu_ctx)
+    Vo, Lo = O.kpca(X, okern)
+    np.testing.assert_allclose(L, Lo[:5], rtol=1e-10)
+    Xc = np.ones((300, 4))
+    V, L = fxb200.kpca(Xc, kern, k=2, ctx=gpu_ctx)
+    assert np.all(np.isfinite(V)) and np.all(np.isfinite(L))
+    assert np.abs(L).max() < 1e-12
+
+
+def test_sigmoid_indefinite_spectrum(gpu_ctx):
+    """tanh kernels are not PSD: the leading (largest algebraic) pairs must still match."""
+    X, _ = mix(900, 10, 4, 2.0, 83)
+    kern, okern = fxb200.SigmoidKernel(0.5, -1.0), O.SigmoidKernel(0.5, -1.0)
+    V, L = fxb200.kpca(X, kern, k=4, ctx=gpu_ctx)
+    Vo, Lo = O.kpca(X, okern)
+    assert Lo[-1] < 0                                   # indefinite indeed
+    np.testing.assert_allclose(L, Lo[:4], rtol=1e-10)
+    assert sin_angle(V, Vo[:, :4]) < 1e-8
+
+
+@pytest.mark.parametrize("m", [1, 127, 129, 300])
+def test_transform_ragged_query_counts(gpu_ctx, m):
+    X, _ = mix(500, 7, 3, 3.0, 84)
+    Z, _ = mix(m, 7, 3, 3.0, 85)
+    for kern, okern in [(fxb200.GaussianKernel(0.1), O.GaussianKernel(0.1)),
+                        (fxb200.PolynomialKernel(0.1, 1.0, 2.0), O.PolynomialKernel(0.1, 1.0, 2.0))]:
+        V, L, model = fxb200.kpca(X, kern, k=3, ctx=gpu_ctx, return_model=True)
+        relclose(model.transform(Z), O.transform_kpca(X, okern, V, Z), 1e-10)
+        model.free()
+    # uncentred fit: transform is the plain projection k(Z,X) V
+    V, L, model = fxb200.kpca(X, fxb200.GaussianKernel(0.1), k=3, center=False, ctx=gpu_ctx, return_model=True)
+    relclose(model.transform(Z), O.kernelmatrix(O.GaussianKernel(0.1), Z, X) @ V, 1e-10)
+    model.free()
+
+
+def test_contexts_are_independent(fx):
+    """Two contexts on the same GPU give identical results (the library keeps no global state
+    beyond its function-attribute caches)."""
+    X, _ = mix(700, 9, 3, 3.0, 86)
+    kern = fx.GaussianKernel(0.1)
+    c1, c2 = fx.Context(0), fx.Context(0)
+    V1, L1 = fx.kpca(X, kern, k=3, ctx=c1)
+    V2, L2 = fx.kpca(X, kern, k=3, ctx=c2)
+    assert np.array_equal(L1, L2) and np.array_equal(V1, V2)      # deterministic, bit for bit
+    c1.close(); c2.close()
