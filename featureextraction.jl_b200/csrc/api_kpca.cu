@@ -228,11 +228,12 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
 
     // eigenvalue post-process: regularize!/perturb! (kpca.jl:53-54) only remap the spectrum,
     // lambda' = ((1-alpha) theta + alpha tr(K~)/n + eps (n-1)) / (n-1)   (kpca.jl:56)
-    double* hp = ctx->pinned + 128;
+    double* hp = ctx->pinned + 2048;                 // k <= 1024 values (pinned scratch holds 4096)
+    double* hs = ctx->pinned + 128;                  // grand mean, trace
     FX_CUDA(cudaMemcpyAsync(hp, theta, k * sizeof(double), cudaMemcpyDeviceToHost, s));
-    FX_CUDA(cudaMemcpyAsync(hp + 64 + 8, g.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(hs, g.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     FX_CUDA(cudaStreamSynchronize(s));
-    const double trace = hp[64 + 8 + 1];
+    const double trace = hs[1];
     st->trace = trace;
     std::vector<double> lam(k);
     for (int i = 0; i < k; ++i)
