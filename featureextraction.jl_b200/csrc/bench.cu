@@ -134,7 +134,9 @@ extern "C" int fx_bench_kernel(fx_ctx* ctx, int which, int64_t n, int64_t d, int
     const double kp_g[3] = {d > 0 ? 1.0 / (double)d : 1.0, 1.0, 3.0};
     const double kp_p[3] = {d > 0 ? 1.0 / (double)d : 1.0, 1.0, 3.0};
     const double kp_s[3] = {d > 0 ? 1.0 / (double)d : 1.0, 0.1, 0.0};
-    const double* kp = kernel_id == 0 ? kp_g : (kernel_id == 1 ? kp_p : kp_s);
+    const double kp_l[3] = {1.0, 0.0, 1.0};          // kernel_id 3 here = linear (polynomial, power 1)
+    const double* kp = kernel_id == 0 ? kp_g : (kernel_id == 1 ? kp_p : (kernel_id == 3 ? kp_l : kp_s));
+    if (kernel_id == 3) kernel_id = 1;
     if (which == 4 || which == 5) {
         FX_TRY(fx_arena_reserve(ctx, 4096));
         fx_arena_reset(ctx);

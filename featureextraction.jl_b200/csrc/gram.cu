@@ -271,6 +271,9 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             attr_set = true;
         }
         long want = 2L * (ctx->sm_count > 0 ? ctx->sm_count : 148);
@@ -279,7 +282,10 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
             case 0: gram_dmma_kernel<0><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
             case 1: gram_dmma_kernel<1><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
             case 2: gram_dmma_kernel<2><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
-            default: gram_dmma_kernel<3><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 3: gram_dmma_kernel<3><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 4: gram_dmma_kernel<4><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 5: gram_dmma_kernel<5><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            default: gram_dmma_kernel<6><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
         }
         ctx->launches++;
     } else {

@@ -223,7 +223,10 @@ int launch_tr(fx_ctx* ctx, const TrParams& p, long m_pad) {
         case 0: return launch_tr2<NBK, 0>(ctx, p, m_pad);
         case 1: return launch_tr2<NBK, 1>(ctx, p, m_pad);
         case 2: return launch_tr2<NBK, 2>(ctx, p, m_pad);
-        default: return launch_tr2<NBK, 3>(ctx, p, m_pad);
+        case 3: return launch_tr2<NBK, 3>(ctx, p, m_pad);
+        case 4: return launch_tr2<NBK, 4>(ctx, p, m_pad);
+        case 5: return launch_tr2<NBK, 5>(ctx, p, m_pad);
+        default: return launch_tr2<NBK, 6>(ctx, p, m_pad);
     }
 }
 
