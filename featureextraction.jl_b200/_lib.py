@@ -64,6 +64,12 @@ PROTOTYPES = {
                                   C.POINTER(SolverOpts), _P, _I64, _P, C.POINTER(_P),
                                   C.POINTER(Stats)]),
     "fx_klda_transform_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I64, C.POINTER(Stats)]),
+    "fx_pca_f64": (C.c_int, [_P, _P, _I64, _I64, _I64, C.c_double, C.c_double, _P, _I64, _P, _P,
+                             C.POINTER(Stats)]),
+    "fx_lda_f64": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, C.c_int, _P, C.c_double, C.c_double,
+                             C.c_double, C.c_double, _P, _I64, _P, C.POINTER(Stats)]),
+    "fx_project_f64": (C.c_int, [_P, _P, _I64, C.c_int, _I64, _P, _I64, _I64, _P, _I64,
+                                 C.POINTER(Stats)]),
     "fx_gram_f64": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _I64, _I64, C.c_int, _D, C.c_int,
                               _P, _I64, C.POINTER(Stats)]),
     "fx_center_f64": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.POINTER(Stats)]),

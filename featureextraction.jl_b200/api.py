@@ -221,6 +221,65 @@ def klda(X, kernel, y, nclass, frequency, alpha_b=0.0, eps_b=0.0, alpha_w=0.0, e
     return tuple(out)
 
 
+# ---- linear solvers of the export list (p <= 512) ----------------------------------------------
+def pca(X, alpha=0.0, eps=0.0, *, ctx=None, return_mean=False):
+    """pca(X, alpha, eps) -> (V, L)   [reference: src/kpca.jl:17-31]"""
+    ctx = ctx or default_context()
+    X = _f64_colmajor(X, "X")
+    n, p = X.shape
+    V = np.empty((p, p), dtype=np.float64, order="F")
+    L = np.empty(p)
+    mu = np.empty(p)
+    st = Stats()
+    check(ctx._lib.fx_pca_f64(ctx._h, _ptr(X), n, p, n, float(alpha), float(eps), _ptr(V), p, _ptr(L),
+                              _ptr(mu), C.byref(st)), "pca")
+    return (V, L, mu) if return_mean else (V, L)
+
+
+def _project(W, Z, ctx, what):
+    ctx = ctx or default_context()
+    W = _f64_colmajor(W, "W"); Z = _f64_colmajor(Z, "Z")
+    p, k = W.shape
+    m = Z.shape[0]
+    if Z.shape[1] != p:
+        raise _lib.DimensionMismatch("%s: Z has %d columns, W has %d rows" % (what, Z.shape[1], p))
+    out = np.empty((m, k), dtype=np.float64, order="F")
+    st = Stats()
+    check(ctx._lib.fx_project_f64(ctx._h, _ptr(W), p, k, p, _ptr(Z), m, m, _ptr(out), m, C.byref(st)), what)
+    return out
+
+
+def transform_pca(W, Z, *, ctx=None):
+    """transform_pca(W, Z) = Z * W   [reference: src/kpca.jl:37]"""
+    return _project(W, Z, ctx, "transform_pca")
+
+
+def transform_lda(W, Z, *, ctx=None):
+    """transform_lda(W, Z) = Z * W   [reference: src/klda.jl:65]"""
+    return _project(W, Z, ctx, "transform_lda")
+
+
+def lda(X, y, nclass, frequency, alpha_b=0.0, eps_b=0.0, alpha_w=0.0, eps_w=0.0, *, ctx=None):
+    """lda!(X, y, k, frequency, ...) -> (V, L) out of place   [reference: src/klda.jl:57-61, with the
+    pencil (Sigma_b, Sigma_w) instead of upstream's (Sigma_b, Sigma_b) at klda.jl:42]"""
+    ctx = ctx or default_context()
+    X = _f64_colmajor(X, "X")
+    n, p = X.shape
+    y = np.ascontiguousarray(y, dtype=np.int64)
+    if y.shape != (n,):
+        raise _lib.DimensionMismatch("X and y must have the same number of rows.")   # klda.jl:16
+    freq = np.ascontiguousarray(frequency, dtype=np.float64)
+    if freq.shape != (nclass,):
+        raise _lib.DimensionMismatch("frequency must have one entry per class")
+    V = np.empty((p, p), dtype=np.float64, order="F")
+    L = np.empty(p)
+    st = Stats()
+    check(ctx._lib.fx_lda_f64(ctx._h, _ptr(X), n, p, n, _ptr(y), int(nclass), _ptr(freq), float(alpha_b),
+                              float(eps_b), float(alpha_w), float(eps_w), _ptr(V), p, _ptr(L), C.byref(st)),
+          "lda")
+    return V, L
+
+
 # ---- building blocks (parity tests, per-kernel benches) --------------------------------------
 def kernelmatrix(kernel, X, Z=None, *, ctx=None, variant=0, return_stats=False):
     """kernelmatrix(k, X) -> n x n  /  kernelmatrix(k, Z, X) -> m x n (pass Z=...)  [kpca.jl:51,65]"""

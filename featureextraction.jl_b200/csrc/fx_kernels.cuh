@@ -137,3 +137,4 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
                      const double* kp, bool center, int variant, FxTimer& tm, fx_stats* st);
 int fx_model_build(fx_ctx* ctx, const GramStage& g, int kernel_id, const double* kp, int k, const double* W,
                    bool centered, bool is_klda, fx_model** out);
+int fx_launch_indicator(fx_ctx* ctx, const int* ydev, int64_t n, int64_t ldr, int cp, double* E);

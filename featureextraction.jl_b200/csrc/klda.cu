@@ -145,6 +145,16 @@ __global__ void symmetrize_kernel(double* S, int cp) {
 
 }  // namespace
 
+int fx_launch_indicator(fx_ctx* ctx, const int* ydev, int64_t n, int64_t ldr, int cp, double* E) {
+    // E covers (n_ld / ldr) rank blocks of ldr rows; here callers pass n_ld = ldr * blocks via the grid
+    const int64_t n_ld = round_up(n, ldr);
+    dim3 grid((unsigned)(n_ld / 128), (unsigned)cp);
+    indicator_kernel<<<grid, 128, 0, ctx->stream>>>(ydev, n, ldr, cp, E);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx,
                                int kernel_id, const double* kparams, const int64_t* y, int nclass,
                                const double* freq, double alpha_b, double eps_b, double alpha_w,

@@ -13,6 +13,8 @@
  *                          (klda.jl:34-61; `klda!` is exported at FeatureExtraction.jl:11
  *                          but never defined)
  *   fx_klda_transform_f64  replaces  transform_klda(X, k, W, Z)        src/klda.jl:71
+ *   fx_pca_f64, fx_lda_f64, fx_project_f64   the linear pca / lda! / transform_pca / transform_lda
+ *                          (src/kpca.jl:8-37, src/klda.jl:34-65) on the same kernels, p <= 512
  *   fx_gram_f64            = MLKernels.kernelmatrix(k, X) / (k, Z, X)  kpca.jl:51,65
  *   fx_center_f64          = MLKernels.centerkernelmatrix!(K)          kpca.jl:52
  *   fx_symm_f64, fx_syevd_small_f64   the two building blocks that stand in for the
@@ -144,6 +146,20 @@ int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t 
                     double* A, int64_t lda, double* lambda, fx_model** model, fx_stats* stats);
 int fx_klda_transform_f64(fx_ctx* ctx, const fx_model* model, const double* Z, int64_t m,
                           int64_t ldz, double* out, int64_t ldo, fx_stats* stats);
+
+/* ---- linear solvers of the same export list (p <= 512), on the same device kernels ---- */
+/* pca(X, alpha, eps) (kpca.jl:17-31): V p x p (descending), lambda p (already / (n-1)),
+ * mean (p, may be NULL) = the column means removed before the decomposition.            */
+int fx_pca_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, int64_t ldx, double alpha,
+               double eps, double* V, int64_t ldv, double* lambda, double* mean, fx_stats* stats);
+/* lda!(X, y, k, frequency, ...) (klda.jl:57-61) with the intended pencil (Sigma_b, Sigma_w):
+ * V p x p generalized eigenvectors, V' Sigma_w V = I (sygvd itype 1), lambda descending.   */
+int fx_lda_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, int64_t ldx, const int64_t* y,
+               int nclass, const double* freq, double alpha_b, double eps_b, double alpha_w,
+               double eps_w, double* V, int64_t ldv, double* lambda, fx_stats* stats);
+/* transform_pca(W, Z) (kpca.jl:37) / transform_lda(W, Z) (klda.jl:65): out (m x k) = Z W.   */
+int fx_project_f64(fx_ctx* ctx, const double* W, int64_t p, int k, int64_t ldw, const double* Z,
+                   int64_t m, int64_t ldz, double* out, int64_t ldo, fx_stats* stats);
 
 /* ---- building blocks, exposed for parity tests and per-kernel benches -------------- */
 /* K (m x n) = k(Z, X); Z == NULL means the symmetric case K = k(X, X) (m = n). */

@@ -394,3 +394,55 @@ def test_contexts_are_independent(fx):
     V2, L2 = fx.kpca(X, kern, k=3, ctx=c2)
     assert np.array_equal(L1, L2) and np.array_equal(V1, V2)      # deterministic, bit for bit
     c1.close(); c2.close()
+
+
+# ------------------------------------------------------------------ linear pca / lda (pinned upstream)
+def test_pca_reference_tests_on_gpu(gpu_ctx):
+    """test_kpca.jl:29-42 through the CUDA path: pca vs eig(Sigma/(n-1)) for every (alpha, eps),
+    transform_pca, and test_kpca.jl:44-56 with BOTH sides on the GPU."""
+    n, p = 20, 5
+    X = np.random.default_rng(6).random((n, p))
+    H = X - X.mean(0)
+    S = H.T @ H / (n - 1)
+    for alpha in (0.0, 0.5):
+        for eps in (0.0, 1.0):
+            V1, D1 = fxb200.pca(X, alpha, eps, ctx=gpu_ctx)
+            D2, V2 = np.linalg.eigh(O.perturb(O.regularize(S, alpha, np.trace(S) / p), eps))
+            np.testing.assert_allclose(np.abs(V1), np.abs(V2[:, ::-1]), atol=1e-10)
+            np.testing.assert_allclose(np.abs(D1), np.abs(D2[::-1]), rtol=1e-12)
+            np.testing.assert_allclose(np.abs(fxb200.transform_pca(V1, X, ctx=gpu_ctx)), np.abs(X @ V2[:, ::-1]),
+                                       atol=1e-10)
+    _V, D1 = fxb200.pca(X, 1.0, 1.0, ctx=gpu_ctx)          # alpha = 1: degenerate, eigenvalues only
+    np.testing.assert_allclose(D1, O.pca(X, 1.0, 1.0)[1], rtol=1e-12)
+    Xc = X - X.mean(0)
+    for eps in (0.0, 1.0):
+        V1, D1 = fxb200.kpca(X, fxb200.PolynomialKernel(1.0, 0.0, 1.0), 0.0, eps, ctx=gpu_ctx)
+        V2, D2 = fxb200.pca(X, 0.0, eps, ctx=gpu_ctx)
+        assert np.abs((V1.T @ Xc @ Xc.T @ V1 / (n - 1))[:p, :p] - V2.T @ S @ V2).max() < 1e-12
+        np.testing.assert_allclose(np.abs(D1)[:p], np.abs(D2), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,p,k", [(12, 3, 4), (500, 37, 5), (3000, 128, 10)])
+def test_lda_matches_oracle(gpu_ctx, n, p, k):
+    rng = np.random.default_rng(91)
+    y = np.repeat(np.arange(1, k + 1), n // k)
+    y = np.concatenate([y, np.full(n - len(y), 1)])
+    X = rng.random((n, p)) + 3.0 * rng.random((k, p))[y - 1]
+    freq = np.bincount(y - 1, minlength=k) / n
+    for (ab, eb, aw, ew) in [(0.0, 0.0, 0.0, 1e-8), (0.2, 0.1, 0.3, 0.05)]:
+        Vo, Lo = O.lda(X, y, k, freq, ab, eb, aw, ew)
+        V, L = fxb200.lda(X, y, k, freq, ab, eb, aw, ew, ctx=gpu_ctx)
+        scale = np.abs(Lo).max()
+        assert np.abs(L - Lo).max() <= 1e-9 * scale
+        nz = int(np.sum(Lo > 1e-8 * scale)) if (ab == 0 and eb == 0) else p
+        nz = min(nz, k - 1) if (ab == 0 and eb == 0) else min(nz, 3)
+        assert sin_angle(V[:, :nz], Vo[:, :nz]) < 1e-6
+        H_b, H_w, _ = O.lda_matrices(X, y, k, freq)
+        _Sb, Sw = O.scatter_matrices(H_b, ab, eb, H_w, aw, ew)
+        np.testing.assert_allclose(V.T @ Sw @ V, np.eye(p), atol=1e-7)       # sygvd normalisation
+        Z = rng.random((33, p))
+        np.testing.assert_allclose(fxb200.transform_lda(V, Z, ctx=gpu_ctx), Z @ V, rtol=1e-12, atol=1e-12)
+    # upstream pencil is singular without eps_w when p > k - 1 ... reported as "not positive definite"
+    if p > n - k:
+        with pytest.raises(fxb200.FxError):
+            fxb200.lda(X, y, k, freq, ctx=gpu_ctx)
