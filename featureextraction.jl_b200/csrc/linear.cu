@@ -41,8 +41,7 @@ __global__ void regularize_kernel(double* A, int lda, int p, double alpha, doubl
     const double shift = alpha * tr / p + eps;
     for (int idx = threadIdx.x; idx < p * p; idx += blockDim.x) {
         const int i = idx % p, j = idx / p;
-        double v = 0.5 * (A[i + (long)j * lda] + A[j + (long)i * lda]);   // syml!: one triangle wins
-        v *= (1.0 - alpha);
+        double v = A[i + (long)j * lda] * (1.0 - alpha);           // own element only (no cross reads)
         if (i == j) v += shift;
         A[i + (long)j * lda] = v;
     }
@@ -153,8 +152,9 @@ extern "C" int fx_pca_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, in
     FX_TRY(fx_launch_ts_nn(ctx, L.ones, 8, M8, 8, pp, 1.0, 1.0, L.X, L.ld, L.ld, 0));
     // Sigma = H'H (kpca.jl:9)
     FX_TRY(fx_launch_ts_tn(ctx, L.X, pp, L.X, pp, L.ld, L.ld, Sig, pp, L.scr, L.scr_doubles, 0));
-    regularize_kernel<<<1, 1024, 0, s>>>(Sig, pp, (int)p, 0.0, 0.0, tr);      // symmetrise + trace
-    ctx->launches++;
+    symmetrize_full_kernel<<<8, 256, 0, s>>>(Sig, pp, (int)p);
+    regularize_kernel<<<1, 1024, 0, s>>>(Sig, pp, (int)p, 0.0, 0.0, tr);      // trace only
+    ctx->launches += 2;
     FX_LAUNCH_CHECK();
     FX_TRY(fx_launch_jacobi(ctx, Sig, pp, (int)p, U, pp, w, Uw, info));
     std::vector<double> hw(p);
@@ -294,9 +294,11 @@ extern "C" int fx_lda_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, in
     // Sigma_b = H_b'H_b, Sigma_w = H_w'H_w (klda.jl:35,39) with shrink / perturb (klda.jl:36-41)
     FX_TRY(fx_launch_ts_tn(ctx, Hb, pp, Hb, pp, ldh, ldh, Sb, pp, L.scr, L.scr_doubles, 0));
     FX_TRY(fx_launch_ts_tn(ctx, L.X, pp, L.X, pp, ld, ld, Sw, pp, L.scr, L.scr_doubles, 0));
+    symmetrize_full_kernel<<<8, 256, 0, s>>>(Sb, pp, (int)p);          // syml! (klda.jl:35,39)
+    symmetrize_full_kernel<<<8, 256, 0, s>>>(Sw, pp, (int)p);
     regularize_kernel<<<1, 1024, 0, s>>>(Sb, pp, (int)p, alpha_b, eps_b, nullptr);
     regularize_kernel<<<1, 1024, 0, s>>>(Sw, pp, (int)p, alpha_w, eps_w, nullptr);
-    ctx->launches += 2;
+    ctx->launches += 4;
     FX_LAUNCH_CHECK();
     // generalized symmetric eigenproblem (common.jl:168-174): Sigma_w = U D U'
     FX_CUDA(cudaMemsetAsync(SbP, 0, (size_t)pp * ldy * 8, s));

@@ -9,7 +9,7 @@
 module FeatureExtractionB200
 
 export GaussianKernel, PolynomialKernel, SigmoidKernel, kpca, transform_kpca, klda, transform_klda,
-       KPCAModel, fit_kpca
+       pca, transform_pca, lda, transform_lda, KPCAModel, fit_kpca
 
 const libfx = get(ENV, "FXB200_LIB", "libfxb200.so")
 
@@ -115,6 +115,44 @@ function klda(X::Matrix{Float64}, κ::Kernel, y::Vector{<:Integer}, k::Integer, 
                 ctx().h, X, n, p, stride(X, 2), kernel_id(κ), kparams(κ), y64, k, frequency, α_b, ϵ_b,
                 α_w, ϵ_w, ncomp, C_NULL, A, n, Λ, C_NULL, C_NULL), "klda")
     (A, Λ)
+end
+
+"`pca(X, α, ϵ)` (src/kpca.jl:17-31) on the device kernels (p <= 512)."
+function pca(X::Matrix{Float64}, α::Float64 = 0.0, ϵ::Float64 = 0.0)
+    n, p = size(X)
+    V = Matrix{Float64}(undef, p, p); Λ = Vector{Float64}(undef, p)
+    check(ccall((:fx_pca_f64, libfx), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, Float64, Ptr{Float64}, Int64,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+                ctx().h, X, n, p, stride(X, 2), α, ϵ, V, p, Λ, C_NULL, C_NULL), "pca")
+    (V, Λ)
+end
+
+"`transform_pca(W, Z)` (src/kpca.jl:37) and `transform_lda(W, Z)` (src/klda.jl:65): Z * W."
+function transform_pca(W::Matrix{Float64}, Z::Matrix{Float64})
+    size(Z, 2) == size(W, 1) || throw(DimensionMismatch("Z and W do not conform"))
+    out = Matrix{Float64}(undef, size(Z, 1), size(W, 2))
+    check(ccall((:fx_project_f64, libfx), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Int64, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Int64,
+                 Ptr{Cvoid}),
+                ctx().h, W, size(W, 1), size(W, 2), stride(W, 2), Z, size(Z, 1), stride(Z, 2), out,
+                size(out, 1), C_NULL), "transform_pca")
+    out
+end
+transform_lda(W::Matrix{Float64}, Z::Matrix{Float64}) = transform_pca(W, Z)
+
+"`lda!(X, y, k, frequency, α_b, ϵ_b, α_w, ϵ_w)` (src/klda.jl:57-61), out of place, pencil (Σ_b, Σ_w)."
+function lda(X::Matrix{Float64}, y::Vector{<:Integer}, k::Integer, frequency::Vector{Float64},
+             α_b = 0.0, ϵ_b = 0.0, α_w = 0.0, ϵ_w = 0.0)
+    n, p = size(X)
+    length(y) == n || throw(DimensionMismatch("X and y must have the same number of rows."))
+    V = Matrix{Float64}(undef, p, p); Λ = Vector{Float64}(undef, p)
+    check(ccall((:fx_lda_f64, libfx), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Int64}, Cint, Ptr{Float64}, Float64, Float64,
+                 Float64, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Cvoid}),
+                ctx().h, X, n, p, stride(X, 2), convert(Vector{Int64}, y), k, frequency, α_b, ϵ_b, α_w, ϵ_w,
+                V, p, Λ, C_NULL), "lda")
+    (V, Λ)
 end
 
 "Reference signature `transform_klda(X, κ, W, Z)` (src/klda.jl:71): κ(Z,X) * W, no centring."
