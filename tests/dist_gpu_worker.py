@@ -52,6 +52,25 @@ def main():
         if rank == 0:
             print("DIST_GPU_OK world=%d n=%d k=%d steps=%d dense=%d comm_ms=%.3f angle=%.1e" %
                   (world, n, k, st["steps"], st["dense_path"], st["comm_ms"], ang), flush=True)
+    # KLDA on the same sharding (indicator K*V, class projector, CG all row-sharded)
+    if len(args) < 3:
+        n, d, c = 1500, 32, 5
+        X, y0 = mix(n, d, c, 2.0, 63)
+        y = y0 + 1
+        freq = np.bincount(y0, minlength=c) / n
+        kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+        K = O.kernelmatrix(okern, X)
+        H_b, H_w, _ = O.lda_matrices(K, y, c, freq)
+        _Sb, Sw = O.scatter_matrices(H_b, 0, 0, H_w, 0, 0)
+        eps_w = 1e-6 * np.trace(Sw) / n
+        Ao, Lo = O.klda(X, okern, y, c, freq, eps_w=eps_w)
+        A, L, st = fxb200.klda(X, kern, y, c, freq, eps_w=eps_w, ctx=ctx, return_stats=True)
+        np.testing.assert_allclose(L, Lo, rtol=1e-7)
+        Qa, _ = np.linalg.qr(A)
+        assert np.linalg.norm(Ao - Qa @ (Qa.T @ Ao), 2) / np.linalg.norm(Ao, 2) < 1e-5
+        if rank == 0:
+            print("DIST_GPU_OK klda world=%d n=%d c=%d cg_iters=%d comm_ms=%.2f" %
+                  (world, n, c, st["cg_iters"], st["comm_ms"]), flush=True)
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
