@@ -446,3 +446,30 @@ def test_lda_matches_oracle(gpu_ctx, n, p, k):
     if p > n - k:
         with pytest.raises(fxb200.FxError):
             fxb200.lda(X, y, k, freq, ctx=gpu_ctx)
+
+
+# ------------------------------------------------------------------ smallest sizes
+@pytest.mark.parametrize("n,d", [(2, 1), (3, 2), (5, 3), (17, 4)])
+def test_kpca_tiny(gpu_ctx, n, d):
+    X = np.random.default_rng(100 + n).random((n, d))
+    for kern, okern in [(fxb200.GaussianKernel(0.7), O.GaussianKernel(0.7)),
+                        (fxb200.PolynomialKernel(1.0, 0.0, 1.0), O.PolynomialKernel(1.0, 0.0, 1.0))]:
+        V, L = fxb200.kpca(X, kern, ctx=gpu_ctx)                   # k = n like the reference
+        Vo, Lo = O.kpca(X, okern)
+        assert V.shape == (n, n)
+        assert np.abs(L - Lo).max() <= 1e-12 * max(np.abs(Lo).max(), 1e-300)
+        assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+
+
+def test_klda_orphan_test_sizes(gpu_ctx):
+    """test/test_klda.jl's sizes (nc = 3 per class, p = 3, k = 4 classes), through KLDA."""
+    rng = np.random.default_rng(8)
+    nc, pp, k = 3, 3, 4
+    y = np.repeat(np.arange(1, k + 1), nc)
+    X = np.vstack([rng.random((nc, pp)) + 10 * rng.random((1, 3)) for _ in range(k)])
+    freq = np.full(k, 1.0 / k)
+    kern, okern = fxb200.GaussianKernel(0.05), O.GaussianKernel(0.05)
+    Ao, Lo = O.klda(X, okern, y, k, freq, eps_w=1e-6)
+    A, L = fxb200.klda(X, kern, y, k, freq, eps_w=1e-6, ctx=gpu_ctx)
+    np.testing.assert_allclose(L, Lo, rtol=1e-6)
+    assert sin_angle(A, Ao) < 1e-4
