@@ -48,6 +48,7 @@ int dmalloc(double** p, size_t doubles) {
 size_t fx_gramstage_bytes(int64_t ld, int64_t n_ld, int64_t d_pad, bool center) {
     size_t t = 0;
     t += fx_align256((size_t)d_pad * n_ld * 8);
+    if (n_ld > ld) t += fx_align256((size_t)d_pad * ld * 8) + fx_align256((size_t)d_pad * n_ld * 8);   // sharded upload
     t += fx_align256((size_t)n_ld * 8) * 4;
     t += fx_align256((size_t)ld * n_ld * 8);
     if (center) t += fx_align256((size_t)(n_ld / 64) * ld * 8);
@@ -70,12 +71,35 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
         fx_set_error("internal: arena too small for the Gram stage");
         return FX_ERR_OOM;
     }
-    tm.begin(&st->h2d_ms);
-    FX_CUDA(cudaMemsetAsync(g.Xp, 0, (size_t)g.d_pad * g.n_ld * 8, s));
-    FX_CUDA(cudaMemcpy2DAsync(g.Xp, g.n_ld * 8, X, ldx * 8, g.n * 8, g.d,
-                              x_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-    tm.end();
-    if (!x_dev) st->h2d_bytes += g.n * g.d * 8;
+    if (!x_dev && ctx->world > 1) {
+        // Host input on several GPUs: every rank uploads only its own row block over PCIe and the
+        // blocks are exchanged over NVLink (all ranks hitting the host with the full X at once is
+        // what dominated the end-to-end time at 8 GPUs).
+        const int G = ctx->world;
+        double* snd = (double*)fx_arena_alloc(ctx, (size_t)g.d_pad * g.ld * 8);
+        double* rcv = (double*)fx_arena_alloc(ctx, (size_t)g.d_pad * g.n_ld * 8);
+        if (!snd || !rcv) { fx_set_error("internal: arena too small for the sharded upload"); return FX_ERR_OOM; }
+        tm.begin(&st->h2d_ms);
+        FX_CUDA(cudaMemsetAsync(snd, 0, (size_t)g.d_pad * g.ld * 8, s));
+        if (g.rows_valid > 0)
+            FX_CUDA(cudaMemcpy2DAsync(snd, g.ld * 8, X + g.row0, ldx * 8, g.rows_valid * 8, g.d,
+                                      cudaMemcpyHostToDevice, s));
+        tm.end();
+        st->h2d_bytes += g.rows_valid * g.d * 8;
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allgather(ctx->comm, snd, rcv, (size_t)g.d_pad * g.ld, s));
+        tm.end();
+        for (int r = 0; r < G; ++r)
+            FX_CUDA(cudaMemcpy2DAsync(g.Xp + (size_t)r * g.ld, g.n_ld * 8, rcv + (size_t)r * g.d_pad * g.ld,
+                                      g.ld * 8, g.ld * 8, g.d_pad, cudaMemcpyDeviceToDevice, s));
+    } else {
+        tm.begin(&st->h2d_ms);
+        FX_CUDA(cudaMemsetAsync(g.Xp, 0, (size_t)g.d_pad * g.n_ld * 8, s));
+        FX_CUDA(cudaMemcpy2DAsync(g.Xp, g.n_ld * 8, X, ldx * 8, g.n * 8, g.d,
+                                  x_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        tm.end();
+        if (!x_dev) st->h2d_bytes += g.n * g.d * 8;
+    }
     FX_CUDA(cudaMemsetAsync(g.colmean, 0, (size_t)g.n_ld * 8, s));
     FX_CUDA(cudaMemsetAsync(g.scal, 0, 256, s));
     FX_TRY(fx_launch_rownorms(ctx, g.Xp, g.n_ld, g.n_ld, g.d_pad, g.norms));
