@@ -102,7 +102,9 @@ def cpu_fit_sample(cfg, n_s, steps=1):
     Gram ~ n^2 d, centring ~ n^2, dsyevd ~ n^3."""
     import oracle as O
     from fxb200.synth import mix
-    from threadpoolctl import threadpool_info
+    from threadpoolctl import threadpool_info, threadpool_limits
+    # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core explicitly
+    threadpool_limits(limits=os.cpu_count(), user_api="blas")
     Xs, _ = mix(n_s, cfg["d"], cfg["c"], cfg["sep"], cfg["seed"])
     okern = {"gaussian": O.GaussianKernel, "polynomial": O.PolynomialKernel,
              "sigmoid": O.SigmoidKernel}[cfg["kernel"]](*cfg["params"])
@@ -329,7 +331,7 @@ def run_ours(args):
                        "lambda": lam_dev.tolist(), "trace": float(trace)},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # CPU baseline: rank 0 at N = 1 only
             cpu = cpu_fit_sample(cfg, args.cpu_sample_n, 1)
             line["cpu_baseline"] = {"value": cpu["extrapolated_s"], "unit": "s", "cores": cpu["cores"],
                                     "kind": "port", "sample": cpu["sample"],
