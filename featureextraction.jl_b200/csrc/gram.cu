@@ -31,6 +31,8 @@ struct GramParams {
     long rows_valid, cols_valid, diag_shift;
     int kt;
     int tiles_x, tiles_y; long tiles_total;
+    int sym;                          // 1: K = map(X X') on one rank -- compute tiles on / right of the
+                                      //    diagonal block only and mirror the strictly-right ones
     KernelMap km;
 };
 
@@ -53,16 +55,22 @@ __device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 1
 
 // Kernel map + row sums + stores for one warp's 64x32 accumulator tile.  EDGE tiles (ragged
 // borders or touching the diagonal) carry the validity masks and the same-point test; interior
-// tiles run the bare arithmetic.
-template <int KID, bool EDGE>
+// tiles run the bare arithmetic.  MIRROR tiles (symmetric mode, strictly right of the diagonal
+// block) also write the transposed element K[j][i] (8 lanes x 8 B = 64 contiguous bytes per
+// column) and the column sums, which are the row-sum partials of the mirrored rows.
+template <int KID, bool EDGE, bool MIRROR>
 __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[8][4][2],
                                               const double (&ni)[8], const double (&nbv)[4][2], long i0,
                                               long j0, int wm, int wn, int g, int t, double* rsb) {
     const long jb = j0 + wn * 32 + 2 * t;
+    double csum[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) csum[nt][0] = csum[nt][1] = 0.0;
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) {
         const long i = i0 + wm * 64 + mt * 8 + g;
         double* krow = p.K + i * p.ldk + jb;
+        double* kcol = p.K + jb * p.ldk + i;             // transposed position of (i, jb)
         const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
         const bool iv = i < p.rows_valid;
         double sacc = 0.0;
@@ -80,6 +88,12 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
                 v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], false);
             }
             *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(v0, v1);
+            if (MIRROR) {
+                kcol[(long)(nt * 8) * p.ldk] = v0;
+                kcol[(long)(nt * 8 + 1) * p.ldk] = v1;
+                csum[nt][0] += v0;
+                csum[nt][1] += v1;
+            }
             sacc += v0 + v1;
         }
         if (p.rowpart) {
@@ -87,6 +101,21 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
             sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
             if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = sacc;
         }
+    }
+    if (MIRROR && p.rowpart) {
+        // column sums over this warp's 64 rows = row-sum partial of mirrored row j for the 64-column
+        // slot [i0 + wm*64, +64) of that row: slot index = 2*(i0/BM) + wm
+        const long slot = 2 * (i0 / BM) + wm;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                double v = csum[nt][q];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (g == 0) p.rowpart[slot * p.rows_pad + jb + nt * 8 + q] = v;
+            }
     }
 }
 
@@ -117,6 +146,7 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
             tile_coords(p, tile, i0, j0, tx);
+            if (p.sym && tx < 2 * (int)(i0 / BM)) continue;       // produced by a mirror store
             for (int kt = 0; kt < KT; ++kt, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);    // passes at once on first use
@@ -138,9 +168,12 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int wm = warp >> 1, wn = warp & 1;
     int it = 0, tcount = 0;
-    for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tcount) {
+    for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         long i0, j0; int tx;
         tile_coords(p, tile, i0, j0, tx);
+        if (p.sym && tx < 2 * (int)(i0 / BM)) continue;
+        const bool mirror = p.sym && tx >= 2 * (int)(i0 / BM) + 2;
+        ++tcount;
         double acc[8][4][2];
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt)
@@ -186,8 +219,13 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
         const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
                           (ig0 < j0 + BN && ig0 + BM > j0);
-        if (edge) gram_epilogue<KID, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
-        else      gram_epilogue<KID, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+        if (mirror) {
+            if (edge) gram_epilogue<KID, true, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+            else      gram_epilogue<KID, false, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+        } else {
+            if (edge) gram_epilogue<KID, true, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+            else      gram_epilogue<KID, false, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+        }
         if (p.rowpart) {
             bar_sync_compute();                  // both column halves of every row are in smem
             p.rowpart[(long)tx * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
@@ -257,6 +295,9 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     p.tiles_x = (int)(a.ldk / BN);
     p.tiles_y = (int)(a.rows_pad / BM);
     p.tiles_total = (long)(a.ldk / BN) * (a.rows_pad / BM);
+    // whole symmetric matrix on one rank: only tiles on / right of the diagonal block are computed
+    p.sym = (a.A == a.B && a.na == a.nb && a.lda == a.ldb && a.diag_shift == 0 && a.rows_pad == a.ldk &&
+             a.rows_valid == a.cols_valid && !a.no_symmetry) ? 1 : 0;
     p.km.id = a.kernel_id; p.km.p0 = a.kp[0]; p.km.p1 = a.kp[1]; p.km.p2 = a.kp[2];
     double tmp[3];
     if (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp)) {
