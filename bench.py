@@ -287,11 +287,11 @@ def run_ours(args):
         center_ms = acc["center_ms"] / K
         symm_ms = acc["symm_ms"] / max(1, acc["symm_launches"])
         gram_flops = 2.0 * ld * n * d                        # algorithmic, per rank, per launch
-        # On one GPU the Gram kernel uses the symmetry of K: only the 128x64 tiles on / right of the
-        # diagonal block are computed, the rest is written by mirror stores.  The roofline uses the
+        # The Gram kernel uses the symmetry of K inside each rank's square diagonal block: only the
+        # 128x64 tiles on / right of the diagonal are computed there, the rest is written by mirror stores.  The roofline uses the
         # EXECUTED flops (so frac <= 1); gram_tflops keeps the algorithmic 2 n^2 d ("no symmetry credit").
         ty = ld // 128
-        exec_frac = (ty + 1.0) / (2.0 * ty) if world == 1 else 1.0
+        exec_frac = 1.0 - (ty - 1.0) / (2.0 * ty * world)     # symmetric part = this rank's diagonal block
         gram_tf_alg = gram_flops / gram_ms / 1e9
         gram_tf = exec_frac * gram_tf_alg
         traffic = None                                       # DRAM bytes per Gram launch from the committed

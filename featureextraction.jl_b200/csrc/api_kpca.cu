@@ -108,7 +108,7 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
     ga.A = g.Xp + g.row0; ga.lda = g.n_ld; ga.B = g.Xp; ga.ldb = g.n_ld;
     ga.na = g.norms + g.row0; ga.nb = g.norms; ga.d_pad = g.d_pad;
     ga.K = g.K; ga.ldk = g.n_ld; ga.rows_pad = g.ld; ga.rows_valid = g.rows_valid;
-    ga.cols_valid = g.n; ga.diag_shift = g.row0; ga.rowpart = g.rowpart;
+    ga.cols_valid = g.n; ga.diag_shift = g.row0; ga.rowpart = g.rowpart; ga.sym_source = 1;
     ga.kernel_id = kernel_id; ga.kp[0] = kp[0]; ga.kp[1] = kp[1]; ga.kp[2] = kp[2];
     tm.begin(&st->gram_ms);
     FX_TRY(fx_launch_gram(ctx, ga, variant));
@@ -350,7 +350,7 @@ extern "C" int fx_gram_f64(fx_ctx* ctx, const double* Z, int64_t m, int64_t ldz,
     GramArgs ga;
     ga.A = Xp; ga.lda = n_pad; ga.B = Zp; ga.ldb = sym ? n_pad : m_ld; ga.na = nx; ga.nb = nz;
     ga.d_pad = d_pad; ga.K = Kd; ga.ldk = m_ld; ga.rows_pad = n_pad; ga.rows_valid = n;
-    ga.cols_valid = m; ga.diag_shift = sym ? 0 : -1; ga.rowpart = nullptr;
+    ga.cols_valid = m; ga.diag_shift = sym ? 0 : -1; ga.rowpart = nullptr; ga.sym_source = sym ? 1 : 0;
     ga.kernel_id = kernel_id; ga.kp[0] = kpv[0]; ga.kp[1] = kpv[1]; ga.kp[2] = kpv[2];
     tm.begin(&st->gram_ms);
     FX_TRY(fx_launch_gram(ctx, ga, variant));

@@ -217,6 +217,7 @@ extern "C" int fx_bench_kernel(fx_ctx* ctx, int which, int64_t n, int64_t d, int
         GramArgs ga;
         ga.A = Xp; ga.lda = n; ga.B = Xp; ga.ldb = n; ga.na = nr; ga.nb = nr; ga.d_pad = d_pad; ga.K = K;
         ga.ldk = n; ga.rows_pad = n; ga.rows_valid = n; ga.cols_valid = n; ga.diag_shift = 0; ga.rowpart = rp;
+        ga.sym_source = (b == 1) ? 0 : 1;           // b = 1: time the all-tiles kernel
         ga.kernel_id = kernel_id; ga.kp[0] = kp[0]; ga.kp[1] = kp[1]; ga.kp[2] = kp[2];
         if (which == 0) return time_loop(ctx, reps, ms_out, [&]() -> int { return fx_launch_gram(ctx, ga, 0); });
         FX_TRY(fx_launch_gram(ctx, ga, 0));

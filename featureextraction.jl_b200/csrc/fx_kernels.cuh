@@ -16,6 +16,7 @@ struct GramArgs {
     int64_t diag_shift;                 // global index of local row 0 (symmetric case), else -1
     double* rowpart;                    // [ldk/64][rows_pad] per-tile partial row sums or null
     int kernel_id; double kp[3];
+    int sym_source = 0;                 // 1: A is the row block [diag_shift, +rows_pad) of B (K symmetric)
     int no_symmetry = 0;                // 1: compute every tile even when the matrix is symmetric
 };
 int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, int64_t d_pad,

@@ -31,8 +31,9 @@ struct GramParams {
     long rows_valid, cols_valid, diag_shift;
     int kt;
     int tiles_x, tiles_y; long tiles_total;
-    int sym;                          // 1: K = map(X X') on one rank -- compute tiles on / right of the
-                                      //    diagonal block only and mirror the strictly-right ones
+    int sym;                          // 1: symmetric source (A == B): inside this rank's square diagonal
+                                      //    block compute only the tiles on / right of the diagonal and
+                                      //    mirror the strictly-right ones; other column blocks in full
     KernelMap km;
 };
 
@@ -70,7 +71,7 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
     for (int mt = 0; mt < 8; ++mt) {
         const long i = i0 + wm * 64 + mt * 8 + g;
         double* krow = p.K + i * p.ldk + jb;
-        double* kcol = p.K + jb * p.ldk + i;             // transposed position of (i, jb)
+        double* kcol = p.K + (jb - p.diag_shift) * p.ldk + i + p.diag_shift;   // transposed position of (i, jb)
         const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
         const bool iv = i < p.rows_valid;
         double sacc = 0.0;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
     if (MIRROR && p.rowpart) {
         // column sums over this warp's 64 rows = row-sum partial of mirrored row j for the 64-column
         // slot [i0 + wm*64, +64) of that row: slot index = 2*(i0/BM) + wm
-        const long slot = 2 * (i0 / BM) + wm;
+        const long slot = p.diag_shift / BN + 2 * (i0 / BM) + wm;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -114,7 +115,7 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
                 v += __shfl_xor_sync(0xffffffffu, v, 8);
                 v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if (g == 0) p.rowpart[slot * p.rows_pad + jb + nt * 8 + q] = v;
+                if (g == 0) p.rowpart[slot * p.rows_pad + (jb - p.diag_shift) + nt * 8 + q] = v;
             }
     }
 }
@@ -146,7 +147,10 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
             tile_coords(p, tile, i0, j0, tx);
-            if (p.sym && tx < 2 * (int)(i0 / BM)) continue;       // produced by a mirror store
+            if (p.sym) {                                          // left of the diagonal inside the
+                const int rel = tx - (int)(p.diag_shift / BN);    // diagonal block: produced by a mirror store
+                if (rel >= 0 && rel < 2 * (int)(i0 / BM)) continue;
+            }
             for (int kt = 0; kt < KT; ++kt, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);    // passes at once on first use
@@ -171,8 +175,9 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         long i0, j0; int tx;
         tile_coords(p, tile, i0, j0, tx);
-        if (p.sym && tx < 2 * (int)(i0 / BM)) continue;
-        const bool mirror = p.sym && tx >= 2 * (int)(i0 / BM) + 2;
+        const int rel = tx - (int)(p.diag_shift / BN);            // column tile relative to the diagonal block
+        if (p.sym && rel >= 0 && rel < 2 * (int)(i0 / BM)) continue;
+        const bool mirror = p.sym && rel >= 2 * (int)(i0 / BM) + 2 && rel < 2 * p.tiles_y;
         ++tcount;
         double acc[8][4][2];
 #pragma unroll
@@ -296,8 +301,8 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     p.tiles_y = (int)(a.rows_pad / BM);
     p.tiles_total = (long)(a.ldk / BN) * (a.rows_pad / BM);
     // whole symmetric matrix on one rank: only tiles on / right of the diagonal block are computed
-    p.sym = (a.A == a.B && a.na == a.nb && a.lda == a.ldb && a.diag_shift == 0 && a.rows_pad == a.ldk &&
-             a.rows_valid == a.cols_valid && !a.no_symmetry) ? 1 : 0;
+    p.sym = (a.sym_source && a.diag_shift >= 0 && a.diag_shift % BM == 0 &&
+             a.diag_shift + a.rows_pad <= a.ldk && !a.no_symmetry) ? 1 : 0;
     p.km.id = a.kernel_id; p.km.p0 = a.kp[0]; p.km.p1 = a.kp[1]; p.km.p2 = a.kp[2];
     double tmp[3];
     if (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp)) {
