@@ -82,6 +82,23 @@ def _kparams(kernel):
     return int(kernel.kernel_id), p
 
 
+def _out_dtype(*arrays):
+    """The reference's functions are generic over T in (Float32, Float64) (test/runtests.jl:7).  This
+    engine computes in float64 only: Float32 inputs are widened on the way in and results are
+    narrowed on the way out, so callers get their element type back (like test_common.jl:66)."""
+    for A in arrays:
+        if isinstance(A, np.ndarray) and A.dtype == np.float32:
+            return np.float32
+    return np.float64
+
+
+def _narrow(dt, *outs):
+    if dt == np.float64:
+        return outs if len(outs) > 1 else outs[0]
+    conv = tuple(o.astype(dt) if isinstance(o, np.ndarray) and o.dtype == np.float64 else o for o in outs)
+    return conv if len(conv) > 1 else conv[0]
+
+
 def make_opts(**kw):
     o = SolverOpts()
     for k, v in kw.items():
@@ -136,6 +153,7 @@ def kpca(X, kernel, alpha=0.0, eps=0.0, *, k=None, center=True, ctx=None, opts=N
     reference) and ``center`` (the reference always centres, kpca.jl:52).
     V has unit-norm columns (sign free), L is descending and already / (n-1)."""
     ctx = ctx or default_context()
+    dt = _out_dtype(X)
     X = _f64_colmajor(X, "X")
     n, p = X.shape
     if k is None:
@@ -150,7 +168,7 @@ def kpca(X, kernel, alpha=0.0, eps=0.0, *, k=None, center=True, ctx=None, opts=N
                                   _ptr(V), n, _ptr(L), C.byref(mh) if return_model else None,
                                   C.byref(st))
     check(rc, "kpca")
-    out = [V, L]
+    out = list(_narrow(dt, V, L))
     if return_model:
         out.append(Model(ctx, mh))
     if return_stats:
@@ -176,9 +194,10 @@ def model_from_components(X, kernel, W, *, center=True, ctx=None):
 def transform_kpca(X, kernel, W, Z, *, center=True, ctx=None):
     """transform_kpca(X, k, W, Z) -> m x k   [reference: src/kpca.jl:64-68, broken upstream]
     = (k(Z,X) - 1 r' - r_z 1' + mu) W, evaluated as k(Z,X) W - 1 (r'W)."""
+    dt = _out_dtype(X, W, Z)
     m = model_from_components(X, kernel, W, center=center, ctx=ctx)
     try:
-        return m.transform(Z)
+        return _narrow(dt, m.transform(Z))
     finally:
         m.free()
 
@@ -225,6 +244,7 @@ def klda(X, kernel, y, nclass, frequency, alpha_b=0.0, eps_b=0.0, alpha_w=0.0, e
 def pca(X, alpha=0.0, eps=0.0, *, ctx=None, return_mean=False):
     """pca(X, alpha, eps) -> (V, L)   [reference: src/kpca.jl:17-31]"""
     ctx = ctx or default_context()
+    dt = _out_dtype(X)
     X = _f64_colmajor(X, "X")
     n, p = X.shape
     V = np.empty((p, p), dtype=np.float64, order="F")
@@ -233,7 +253,7 @@ def pca(X, alpha=0.0, eps=0.0, *, ctx=None, return_mean=False):
     st = Stats()
     check(ctx._lib.fx_pca_f64(ctx._h, _ptr(X), n, p, n, float(alpha), float(eps), _ptr(V), p, _ptr(L),
                               _ptr(mu), C.byref(st)), "pca")
-    return (V, L, mu) if return_mean else (V, L)
+    return _narrow(dt, V, L, mu) if return_mean else _narrow(dt, V, L)
 
 
 def _project(W, Z, ctx, what):

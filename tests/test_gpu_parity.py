@@ -473,3 +473,16 @@ def test_klda_orphan_test_sizes(gpu_ctx):
     A, L = fxb200.klda(X, kern, y, k, freq, eps_w=1e-6, ctx=gpu_ctx)
     np.testing.assert_allclose(L, Lo, rtol=1e-6)
     assert sin_angle(A, Ao) < 1e-4
+
+
+def test_float32_inputs_keep_their_eltype(gpu_ctx):
+    """The reference is generic over (Float32, Float64) (test/runtests.jl:7, eltype checks at
+    test_common.jl:66,73): Float32 in -> Float32 out, computed in float64 underneath."""
+    X = np.random.default_rng(7).random((20, 5)).astype(np.float32)
+    V, D = fxb200.kpca(X, fxb200.PolynomialKernel(1.0, 0.0, 1.0), ctx=gpu_ctx)
+    assert V.dtype == np.float32 and D.dtype == np.float32
+    V2, D2 = fxb200.pca(X, ctx=gpu_ctx)
+    assert V2.dtype == np.float32 and D2.dtype == np.float32
+    np.testing.assert_allclose(np.abs(D)[:5], np.abs(D2), rtol=1e-5)
+    T = fxb200.transform_kpca(X, fxb200.GaussianKernel(0.5), V[:, :2].astype(np.float32), X, ctx=gpu_ctx)
+    assert T.dtype == np.float32 and T.shape == (20, 2)
