@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
     double* Wsm = smem + TST * TSTAGE_D;                           // 2 x [NBK*8][WS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Wsm + 2 * NBK * 8 * WS);
+    double* nxs = Wsm + 2 * NBK * 8 * WS;                          // 2 x [TN] squared norms of the tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(nxs + 2 * TN);
     uint64_t* full = bars;            // [TST]
     uint64_t* empty = bars + TST;     // [TST]
     uint64_t* wfull = bars + 2 * TST; // [2]
@@ -62,10 +63,11 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
             const long j0 = (long)tile * TN;
             const int wi = tile - t_begin, ws = wi & 1;
             mbar_wait(&wempty[ws], ((wi >> 1) & 1) ^ 1);
-            if (lane == 0) mbar_arrive_expect_tx(&wfull[ws], NBK * 8 * TN * 8);
+            if (lane == 0) mbar_arrive_expect_tx(&wfull[ws], NBK * 8 * TN * 8 + (KID == 0 ? TN * 8 : 0));
             __syncwarp();
             for (int c = lane; c < NBK * 8; c += 32)
                 bulk_g2s(Wsm + (ws * NBK * 8 + c) * WS, p.W + (long)c * p.ldw + j0, TN * 8, &wfull[ws]);
+            if (KID == 0 && lane == 0) bulk_g2s(nxs + ws * TN, p.nx + j0, TN * 8, &wfull[ws]);
             for (int kt = 0; kt < KT; ++kt, ++it) {
                 const int s = it % TST;
                 mbar_wait(&empty[s], ((it / TST) & 1) ^ 1);
@@ -127,13 +129,15 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
-        // kernel map in registers
+        // kernel map in registers (the tile's W slab and norms were staged by the producer)
+        const int wi = tile - t_begin, ws = wi & 1;
+        mbar_wait(&wfull[ws], (wi >> 1) & 1);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             const long j = j0 + nt * 8 + 2 * t;
             double nx0 = 0.0, nx1 = 0.0;
             if (gauss) {
-                const double2 v = *reinterpret_cast<const double2*>(p.nx + j);
+                const double2 v = *reinterpret_cast<const double2*>(nxs + ws * TN + nt * 8 + 2 * t);
                 nx0 = v.x; nx1 = v.y;
             }
             const bool v0 = j < p.n_valid, v1 = (j + 1) < p.n_valid;
@@ -145,8 +149,6 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
         }
 
         // second contraction: acc2 += Ktile (16 x 64 per warp) * W[j0:j0+64, :]
-        const int wi = tile - t_begin, ws = wi & 1;
-        mbar_wait(&wfull[ws], (wi >> 1) & 1);
         const double* Wt = Wsm + (size_t)ws * NBK * 8 * WS + g * WS + 2 * t;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -205,7 +207,7 @@ __global__ void transform_naive_kernel(const TrParams p, int d_pad, long m_pad) 
 
 template <int NBK, int KID>
 int launch_tr2(fx_ctx* ctx, const TrParams& p, long m_pad) {
-    constexpr int SMEM = (TST * TSTAGE_D + 2 * NBK * 8 * WS) * 8 + 128;
+    constexpr int SMEM = (TST * TSTAGE_D + 2 * NBK * 8 * WS + 2 * TN) * 8 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         FX_CUDA(cudaFuncSetAttribute(transform_kernel<NBK, KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
