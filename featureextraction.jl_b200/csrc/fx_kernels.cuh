@@ -71,16 +71,21 @@ int fx_launch_ts_nn(fx_ctx* ctx, const double* A, int ma, const double* M, int l
 // Parallel cyclic Jacobi on a device matrix A (m x m, lda), eigenvalues descending in w,
 // eigenvectors (columns, same order) in Vout (ldv).  A is destroyed.  info[0] = sweeps,
 // info[1] = converged flag.
+// `need` (device int, may be null): the kernel returns at once when *need == 0.
 int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int ldv, double* w,
-                     double* Vwork, int* info);
+                     double* Vwork, int* info, const int* need = nullptr);
+// CholQR fast path of the block orthonormalisation; sets *need_svqb = 1 when a pivot < thr
+int fx_launch_chol_factors(fx_ctx* ctx, const double* G, int ldg, int b, double thr, double* M, double* Cfac,
+                           int* need_svqb, int* ndef);
 size_t fx_jacobi_work_doubles(int m);
 int fx_launch_hash_fill(fx_ctx* ctx, double* W, int64_t ld, int64_t rows_valid, int64_t row0,
                         int cols, uint64_t seed);
 // SVQB helpers (single CTA)
-int fx_launch_svqb_prep(fx_ctx* ctx, const double* G, int ldg, int b, double* Gs, double* dscale);
+int fx_launch_svqb_prep(fx_ctx* ctx, const double* G, int ldg, int b, double* Gs, double* dscale,
+                        const int* need = nullptr);
 int fx_launch_svqb_factors(fx_ctx* ctx, const double* U, int ldu, const double* lam,
                            const double* dscale, int b, double tol, double* M, double* Cfac,
-                           int* ndef);
+                           int* ndef, const int* need = nullptr);
 // C = A(b x b) * B(b x b), all column-major ld b
 int fx_launch_small_matmul(fx_ctx* ctx, const double* A, const double* B, int b, double* C);
 // T[:mq, m0:m0+b] = H (mq x b, ldh); T[m0:m0+b, :m0] = H[:m0]'; diagonal block symmetrised

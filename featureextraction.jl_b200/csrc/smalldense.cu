@@ -63,8 +63,9 @@ __device__ __forceinline__ void schur_rotation(double app, double aqq, double ap
 template <bool SMEM_A, bool SMEM_V>
 __global__ void __launch_bounds__(1024, 1) jacobi_kernel(double* Ag, int lda_g, int m, double* Vg, int ldvg,
                                                          double* w, double* Vout, int ldvo, int* info,
-                                                         int max_sweeps) {
+                                                         int max_sweeps, const int* need) {
     extern __shared__ __align__(16) double sm[];
+    if (need && *need == 0) return;               // the Cholesky fast path already produced the factors
     __shared__ double red[33];
     __shared__ int s_rank[1024];
     __shared__ double rot_c[512], rot_s[512];     // written and read by the pair's owner warp only
@@ -180,8 +181,70 @@ __global__ void hash_fill_kernel(double* W, long ld, long rows_valid, long row0,
     W[(long)c * ld + i] = v;
 }
 
-__global__ void svqb_prep_kernel(const double* G, int ldg, int b, double* Gs, double* dscale) {
+// Fast path of the block orthonormalisation: Cholesky of the diagonally scaled Gram matrix
+// (CholQR).  G = D Gs D, Gs = L L'  =>  W_orth = W D^-1 L^-T,  W = W_orth (L' D).
+// Writes M = D^-1 L^-T and Cfac = L' D and need_svqb = 0; if a pivot falls below `thr` (block
+// numerically rank deficient / ill conditioned) writes need_svqb = 1 and the SVQB (Jacobi)
+// kernels that follow do the work instead -- they return at once when need_svqb == 0.
+__global__ void __launch_bounds__(256) chol_factors_kernel(const double* G, int ldg, int b, double thr,
+                                                           double* M, double* Cfac, int* need_svqb,
+                                                           int* ndef) {
+    extern __shared__ __align__(16) double chol_sm[];
+    double (*L)[65] = reinterpret_cast<double (*)[65]>(chol_sm);
+    double (*Li)[65] = reinterpret_cast<double (*)[65]>(chol_sm + 64 * 65);
+    double* d = chol_sm + 2 * 64 * 65;
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    if (tid < b) d[tid] = sqrt(fmax(G[tid + (long)tid * ldg], 1e-300));
+    __syncthreads();
+    for (int idx = tid; idx < b * b; idx += blockDim.x) {
+        const int i = idx % b, j = idx / b;
+        L[i][j] = 0.5 * (G[i + (long)j * ldg] + G[j + (long)i * ldg]) / (d[i] * d[j]);
+        Li[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < b; ++j) {
+        const double piv = L[j][j];
+        if (!(piv > thr)) { if (tid == 0) bad = 1; break; }       // uniform: every thread reads the same value
+        const double inv = rsqrt(piv);
+        __syncthreads();
+        for (int i = j + tid; i < b; i += blockDim.x) L[i][j] *= inv;        // column j (incl. diagonal -> sqrt)
+        __syncthreads();
+        const int rem = b - j - 1;
+        for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
+            const int i = j + 1 + idx % rem, k = j + 1 + idx / rem;
+            if (k <= i) L[i][k] -= L[i][j] * L[k][j];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (bad) {
+        if (tid == 0) *need_svqb = 1;
+        return;
+    }
+    // Li = L^-1 by forward substitution, one thread per column of the identity
+    if (tid < b) {
+        const int c = tid;
+        for (int i = c; i < b; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; ++k) s -= L[i][k] * Li[k][c];
+            Li[i][c] = s / L[i][i];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < b * b; idx += blockDim.x) {
+        const int i = idx % b, j = idx / b;
+        // M = D^-1 L^-T : M[i][j] = Li[j][i] / d[i] (upper triangular);  Cfac = L' D : Cfac[i][j] = L[j][i] d[j]
+        M[i + j * b] = (j >= i) ? Li[j][i] / d[i] : 0.0;
+        Cfac[i + j * b] = (j >= i) ? L[j][i] * d[j] : 0.0;
+    }
+    if (tid == 0) { *need_svqb = 0; if (ndef) *ndef = 0; }
+}
+
+__global__ void svqb_prep_kernel(const double* G, int ldg, int b, double* Gs, double* dscale, const int* need) {
     __shared__ double d[64];
+    if (need && *need == 0) return;
     const int tid = threadIdx.x;
     if (tid < b) {
         const double gii = G[tid + (long)tid * ldg];
@@ -199,9 +262,10 @@ __global__ void svqb_prep_kernel(const double* G, int ldg, int b, double* Gs, do
 
 // M = D^-1 U L^-1/2 (W_orth = W M),  Cfac = L^1/2 U' D (W = W_orth Cfac)
 __global__ void svqb_factors_kernel(const double* U, int ldu, const double* lam, const double* dscale,
-                                    int b, double tol, double* M, double* Cfac, int* ndef) {
+                                    int b, double tol, double* M, double* Cfac, int* ndef, const int* need) {
     __shared__ double l[64];
     __shared__ int cnt;
+    if (need && *need == 0) return;
     const int tid = threadIdx.x;
     if (tid == 0) cnt = 0;
     __syncthreads();
@@ -276,7 +340,7 @@ __global__ void bias_kernel(const double* colmean, const double* W, long ld, lon
 size_t fx_jacobi_work_doubles(int m) { return (size_t)m * m; }
 
 int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int ldv, double* w,
-                     double* Vwork, int* info) {
+                     double* Vwork, int* info, const int* need) {
     if (m < 1 || m > 1024) {
         fx_set_error("jacobi: order %d out of range", m);
         return FX_ERR_CUDA;
@@ -295,9 +359,9 @@ int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int l
         if (mode == 1) FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[mode] = smem;
     }
-    if (mode == 2) jacobi_kernel<true, true><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40);
-    else if (mode == 1) jacobi_kernel<true, false><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40);
-    else jacobi_kernel<false, false><<<1, threads, 0, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40);
+    if (mode == 2) jacobi_kernel<true, true><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40, need);
+    else if (mode == 1) jacobi_kernel<true, false><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40, need);
+    else jacobi_kernel<false, false><<<1, threads, 0, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40, need);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;
@@ -313,8 +377,26 @@ int fx_launch_hash_fill(fx_ctx* ctx, double* W, int64_t ld, int64_t rows_valid, 
     return 0;
 }
 
-int fx_launch_svqb_prep(fx_ctx* ctx, const double* G, int ldg, int b, double* Gs, double* dscale) {
-    svqb_prep_kernel<<<1, 256, 0, ctx->stream>>>(G, ldg, b, Gs, dscale);
+int fx_launch_chol_factors(fx_ctx* ctx, const double* G, int ldg, int b, double thr, double* M, double* Cfac,
+                           int* need_svqb, int* ndef) {
+    if (b < 1 || b > 64) {
+        fx_set_error("chol_factors: block width %d out of range", b);
+        return FX_ERR_CUDA;
+    }
+    const size_t smem = (2 * 64 * 65 + 64) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        FX_CUDA(cudaFuncSetAttribute(chol_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    chol_factors_kernel<<<1, 256, smem, ctx->stream>>>(G, ldg, b, thr, M, Cfac, need_svqb, ndef);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_svqb_prep(fx_ctx* ctx, const double* G, int ldg, int b, double* Gs, double* dscale, const int* need) {
+    svqb_prep_kernel<<<1, 256, 0, ctx->stream>>>(G, ldg, b, Gs, dscale, need);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;
@@ -322,8 +404,8 @@ int fx_launch_svqb_prep(fx_ctx* ctx, const double* G, int ldg, int b, double* Gs
 
 int fx_launch_svqb_factors(fx_ctx* ctx, const double* U, int ldu, const double* lam,
                            const double* dscale, int b, double tol, double* M, double* Cfac,
-                           int* ndef) {
-    svqb_factors_kernel<<<1, 256, 0, ctx->stream>>>(U, ldu, lam, dscale, b, tol, M, Cfac, ndef);
+                           int* ndef, const int* need) {
+    svqb_factors_kernel<<<1, 256, 0, ctx->stream>>>(U, ldu, lam, dscale, b, tol, M, Cfac, ndef, need);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;

@@ -104,9 +104,12 @@ int svqb_pass(fx_ctx* ctx, const Work& w, const double* src, double* dst, int64_
         tm.end();
     }
     tm.begin(&st->rr_ms);
-    FX_TRY(fx_launch_svqb_prep(ctx, w.G, b, b, w.Gs, w.dscale));
-    FX_TRY(fx_launch_jacobi(ctx, w.Gs, b, b, w.U, b, w.lamb, w.Uw, w.info + 2));
-    FX_TRY(fx_launch_svqb_factors(ctx, w.U, b, w.lamb, w.dscale, b, 1e-14, Mout, Cout, w.info + 4));
+    // CholQR when the block is well conditioned (pivots of the scaled Gram > 1e-8), else SVQB: the
+    // three kernels after the Cholesky return immediately unless it raised the flag (w.info + 6)
+    FX_TRY(fx_launch_chol_factors(ctx, w.G, b, b, 1e-8, Mout, Cout, w.info + 6, w.info + 4));
+    FX_TRY(fx_launch_svqb_prep(ctx, w.G, b, b, w.Gs, w.dscale, w.info + 6));
+    FX_TRY(fx_launch_jacobi(ctx, w.Gs, b, b, w.U, b, w.lamb, w.Uw, w.info + 2, w.info + 6));
+    FX_TRY(fx_launch_svqb_factors(ctx, w.U, b, w.lamb, w.dscale, b, 1e-14, Mout, Cout, w.info + 4, w.info + 6));
     tm.end();
     tm.begin(&st->ortho_ms);
     FX_TRY(fx_launch_ts_nn(ctx, src, b, Mout, b, b, 1.0, 0.0, dst, ld, ld, variant));
