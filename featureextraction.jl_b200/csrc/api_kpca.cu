@@ -128,14 +128,22 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
         }
         tm.begin(&st->center_ms);
         FX_TRY(fx_launch_means(ctx, g.rowsum, g.n, g.n_ld, g.colmean, g.scal));
-        FX_TRY(fx_launch_center(ctx, g.K, g.n_ld, g.rows_valid, g.n, g.row0, g.colmean, g.scal));
+        if (!g.defer_center) {
+            FX_TRY(fx_launch_center(ctx, g.K, g.n_ld, g.rows_valid, g.n, g.row0, g.colmean, g.scal));
+            st->center_launches++;
+        }
         tm.end();
-        st->center_launches++;
+        if (g.defer_center) return 0;
     }
+    return fx_gramstage_trace(ctx, g, tm, st);
+}
+
+// trace of the (centred) matrix over all ranks -> g.scal[1]
+int fx_gramstage_trace(fx_ctx* ctx, GramStage& g, FxTimer& tm, fx_stats* st) {
     FX_TRY(fx_launch_trace(ctx, g.K, g.n_ld, g.rows_valid, g.row0, g.scal + 1));
     if (ctx->world > 1) {
         tm.begin(&st->comm_ms);
-        FX_TRY(fxcomm_allreduce_sum(ctx->comm, g.scal + 1, 1, s));
+        FX_TRY(fxcomm_allreduce_sum(ctx->comm, g.scal + 1, 1, ctx->stream));
         tm.end();
     }
     return 0;
@@ -236,6 +244,9 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
 
     GramStage g;
     g.n = n; g.d = d; g.ld = ld; g.n_ld = n_ld; g.d_pad = d_pad; g.row0 = row0; g.rows_valid = rows_valid;
+    // the block solver's first K*V pass does the centring (one read of K for both); the dense
+    // path and the naive cross-check variant centre in a pass of their own
+    g.defer_center = center != 0 && !dense && o.variant == 0;
     FX_TRY(fx_gramstage_run(ctx, g, X, on_dev, ldx, kernel_id, kpv, center != 0, o.variant, tm, st));
 
     double* Vout = (double*)fx_arena_alloc(ctx, (size_t)kp * n_ld * 8);
@@ -245,10 +256,12 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     EigArgs ea;
     ea.K = g.K; ea.ldk = n_ld; ea.n = n; ea.ld = ld; ea.n_ld = n_ld; ea.row0 = row0;
     ea.rows_valid = rows_valid; ea.k = k; ea.opts = o; ea.Vout = Vout; ea.theta = theta;
+    if (g.defer_center) { ea.center_colmean = g.colmean; ea.center_grand = g.scal; }
     tm.begin(&st->eig_ms);
     int eig_rc = dense ? fx_eig_dense(ctx, ea, tm, st) : fx_eig_topk(ctx, ea, tm, st);
     tm.end();
     if (eig_rc != 0 && eig_rc != FX_ERR_NOT_CONVERGED) return eig_rc;
+    if (g.defer_center) FX_TRY(fx_gramstage_trace(ctx, g, tm, st));
 
     // eigenvalue post-process: regularize!/perturb! (kpca.jl:53-54) only remap the spectrum,
     // lambda' = ((1-alpha) theta + alpha tr(K~)/n + eps (n-1)) / (n-1)   (kpca.jl:56)

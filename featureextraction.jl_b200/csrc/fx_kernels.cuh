@@ -51,6 +51,12 @@ struct SymmArgs {
     double* Y;                          // [bcols][rows_pad]
     double* Ypart;                      // scratch >= splits*bcols*rows_pad doubles (splits>1)
     int splits;                         // k-splits chosen by fx_symm_splits
+    // Fused centring (first pass of a fit): when center_colmean != null, K still holds the
+    // uncentred matrix; the kernel centres every element it streams, writes it back IN PLACE
+    // (K is then an in/out argument) and multiplies with the centred values.
+    const double* center_colmean = nullptr;   // [ldk] column means (index = global sample)
+    const double* center_grand = nullptr;     // device scalar
+    int64_t rows_valid = 0, cols_valid = 0, row0 = 0;
 };
 int fx_symm_splits(fx_ctx* ctx, int64_t rows_pad, int64_t ldk);
 int fx_launch_symm(fx_ctx* ctx, const SymmArgs& a, int variant);
@@ -120,6 +126,10 @@ struct EigArgs {
     fx_solver_opts opts;
     double* Vout;                       // device, column-major [k][n_ld] (all rows, gathered)
     double* theta;                      // device, k Ritz values (unscaled), descending
+    // Deferred centring (fx_eig_topk only): when non-null, K is NOT yet centred and the first
+    // K*V pass centres it in place (symm.cu CENTER variant); K is centred when the call returns.
+    const double* center_colmean = nullptr;
+    const double* center_grand = nullptr;
 };
 int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st);
 int fx_eig_dense(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st);
@@ -138,7 +148,12 @@ int fx_launch_fill(fx_ctx* ctx, double* p, int64_t n, double v);
 struct GramStage {
     int64_t n, d, ld, n_ld, d_pad, row0, rows_valid;
     double *Xp, *norms, *K, *rowpart, *rowsum, *colmean, *scal;   // scal[0]=grand mean, scal[1]=trace
+    // Set by the caller before fx_gramstage_run: compute the means but leave K uncentred -- the
+    // eigensolver's first K*V pass centres it in place (EigArgs::center_colmean); the caller
+    // then finishes with fx_gramstage_trace.
+    bool defer_center = false;
 };
+int fx_gramstage_trace(fx_ctx* ctx, GramStage& g, FxTimer& tm, fx_stats* st);
 size_t fx_gramstage_bytes(int64_t ld, int64_t n_ld, int64_t d_pad, bool center);
 int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int64_t ldx, int kernel_id,
                      const double* kp, bool center, int variant, FxTimer& tm, fx_stats* st);

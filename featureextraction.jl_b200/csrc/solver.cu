@@ -177,10 +177,21 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
         sa.K = a.K; sa.ldk = a.ldk; sa.rows_pad = ld; sa.V = Vsrc; sa.ldr = ld;
         sa.v_rank_stride = (int64_t)b * ld; sa.bcols = b; sa.Y = w.Wa; sa.Ypart = w.Ypart;
         sa.splits = w.splits;
-        tm.begin(&st->symm_ms);
-        FX_TRY(fx_launch_symm(ctx, sa, variant));
-        tm.end();
-        st->symm_launches++;
+        if (steps == 0 && a.center_colmean) {
+            // deferred centring: this pass centres K in place while it multiplies (one read of K
+            // serves both); it is booked as the centring pass
+            sa.center_colmean = a.center_colmean; sa.center_grand = a.center_grand;
+            sa.rows_valid = a.rows_valid; sa.cols_valid = a.n; sa.row0 = a.row0;
+            tm.begin(&st->center_ms);
+            FX_TRY(fx_launch_symm(ctx, sa, variant));
+            tm.end();
+            st->center_launches++;
+        } else {
+            tm.begin(&st->symm_ms);
+            FX_TRY(fx_launch_symm(ctx, sa, variant));
+            tm.end();
+            st->symm_launches++;
+        }
         steps++;
         // 3-5. CGS2 against [Q Qn]; H accumulates both passes
         FX_TRY(project_out(ctx, w, mq, w.Wa, ld, w.H, variant, tm, st));
