@@ -254,6 +254,7 @@ def run_ours(args):
         fit_dev()
     ms_dev, acc, launches = timed(fit_dev, args.steps)
     maxres, conv, block, trace = st.max_residual, st.converged, st.block, st.trace
+    peer_access = ctx.peer_access
     lam_dev = Ld.cpu().numpy().copy()
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -264,6 +265,13 @@ def run_ours(args):
     lam_host = Lh.numpy().copy()
 
     # live roofline denominators on this GPU: fp64 DMMA issue peak and stream copy
+    # per-rank Gram / collective time (ranks wait for the slowest one inside comm_ms)
+    per_rank = None
+    if dist is not None:
+        t = torch.tensor([acc["gram_ms"] / args.steps, acc["comm_ms"] / args.steps], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        per_rank = {"gram_ms": [round(float(o[0]), 3) for o in out], "comm_ms": [round(float(o[1]), 3) for o in out]}
     peak_dmma = peak_copy = None
     cpu = None
     if rank == 0:
@@ -290,8 +298,9 @@ def run_ours(args):
         # The Gram kernel uses the symmetry of K inside each rank's square diagonal block: only the
         # 128x64 tiles on / right of the diagonal are computed there, the rest is written by mirror stores.  The roofline uses the
         # EXECUTED flops (so frac <= 1); gram_tflops keeps the algorithmic 2 n^2 d ("no symmetry credit").
-        ty = ld // 128
-        exec_frac = 1.0 - (ty - 1.0) / (2.0 * ty * world)     # symmetric part = this rank's diagonal block
+        # With several ranks and NVLink peer mappings the off-diagonal blocks are shared out as well.
+        t_exec, t_all = fxb200.sharding.gram_tiles_executed(n, world, 0, peer_access)
+        exec_frac = t_exec / t_all
         gram_tf_alg = gram_flops / gram_ms / 1e9
         gram_tf = exec_frac * gram_tf_alg
         traffic = None                                       # DRAM bytes per Gram launch from the committed
@@ -312,19 +321,23 @@ def run_ours(args):
             "gpu_launches": int(launches + launches_h),
             "gram_tflops": gram_tf_alg * world,
             "gram_executed_fraction": exec_frac,
+            "peer_access": bool(peer_access),
             "roofline": {"bound": "tensor", "kernel": "gram_dmma_kernel", "achieved": gram_tf,
                          "peak": peak_dmma, "unit": "TFLOP/s", "frac": gram_tf / peak_dmma,
                          "traffic": traffic,
                          "peak_source": "fp64 DMMA.8x8x4 issue-rate microbenchmark measured live in this run "
                                         "(fx_bench_kernel 4); MEASURED_PEAKS.json has no fp64 entry",
                          "algorithmic": "2*rows_per_rank*n*d flops per launch = %.4g; executed = %.4g of it "
-                                        "(symmetric tiles mirrored on one GPU)" % (gram_flops, exec_frac)},
+                                        "(symmetric tiles mirrored, across ranks over NVLink peer stores when "
+                                        "peer_access)" % (gram_flops, exec_frac)},
             "roofline_secondary": [
-                {"kernel": "center_kernel", "bound": "hbm", "achieved": 16.0 * ld * n / center_ms / 1e6,
+                {"kernel": "symm_dmma_kernel<CENTER> (centring fused with the first K*V pass)", "bound": "hbm",
+                 "achieved": 16.0 * ld * n / center_ms / 1e6,
                  "peak": hbm_peak, "unit": "GB/s", "frac": 16.0 * ld * n / center_ms / 1e6 / hbm_peak,
                  "frac_of_nominal_8TBs": 16.0 * ld * n / center_ms / 1e6 / 8000.0,
                  "peak_source": hbm_src, "copy_GBs_live": peak_copy,
-                 "note": "center_ms also covers the row-sum partial reduce and the means kernel"},
+                 "note": "one read + one write of K; center_ms also covers the row-sum partial reduce and the "
+                         "means kernel; the K*V product of this pass is free (HBM-bound)"},
                 {"kernel": "symm_dmma_kernel", "bound": "hbm", "achieved": 8.0 * ld * n / symm_ms / 1e6,
                  "peak": hbm_peak, "unit": "GB/s", "frac": 8.0 * ld * n / symm_ms / 1e6 / hbm_peak,
                  "frac_of_nominal_8TBs": 8.0 * ld * n / symm_ms / 1e6 / 8000.0,
@@ -333,6 +346,7 @@ def run_ours(args):
             "phases_ms_per_fit": {k2: acc[k2] / K for k2 in ("gram_ms", "center_ms", "symm_ms", "ortho_ms",
                                                              "rr_ms", "comm_ms", "eig_ms")},
             "e2e_phases_ms_per_fit": {k2: acc_h[k2] / K for k2 in ("h2d_ms", "d2h_ms", "gram_ms", "eig_ms")},
+            "per_rank_ms_per_fit": per_rank,
             "solver": {"kv_passes": int(acc["steps"]), "block": int(block), "converged": int(conv),
                        "max_rel_residual": float(maxres)},
             "parity": {"host_vs_device_lambda_max_rel_diff": float(np.abs(lam_host / lam_dev - 1).max()),

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "fx_init_distributed": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     "fx_set_stream": (C.c_int, [_P, _P]),
     "fx_ctx_info": (C.c_int, [_P] + [C.POINTER(C.c_int)] * 4),
+    "fx_ctx_peer_access": (C.c_int, [_P]),
     "fx_shutdown": (None, [_P]),
     "fx_kpca_fit_f64": (C.c_int, [_P, _P, _I64, _I64, _I64, C.c_int, _D, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.POINTER(SolverOpts), _P, _I64, _P,

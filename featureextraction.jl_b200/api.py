@@ -44,6 +44,12 @@ class Context:
         check(lib.fx_comm_unique_id(buf), "fx_comm_unique_id")
         return bytes(buf.raw)
 
+    @property
+    def peer_access(self):
+        """True if the last collective fit shared the symmetric blocks of K between ranks over
+        NVLink peer mappings (fx_ctx_peer_access)."""
+        return bool(self._lib.fx_ctx_peer_access(self._h))
+
     def set_stream(self, cuda_stream_ptr):
         check(self._lib.fx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "fx_set_stream")
 

@@ -1,5 +1,6 @@
 // api_core.cu -- contexts, error text, device arena, event timers.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "fx_kernels.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -19,7 +20,11 @@ int fx_arena_reserve(fx_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->arena_cap) return 0;
     if (ctx->arena) {
         FX_CUDA(cudaStreamSynchronize(ctx->stream));
-        FX_CUDA(cudaFree(ctx->arena));
+        // an arena whose IPC handle went out to peers may still be mapped there: park it until
+        // the next collective exchange has made every peer drop the mapping
+        if (ctx->arena_exported) ctx->retired.push_back(ctx->arena);
+        else FX_CUDA(cudaFree(ctx->arena));
+        ctx->arena_exported = false;
         ctx->arena = nullptr;
         ctx->arena_cap = 0;
     }
@@ -32,6 +37,94 @@ int fx_arena_reserve(fx_ctx* ctx, size_t bytes) {
     }
     ctx->arena_cap = bytes;
     ctx->arena_off = 0;
+    ctx->arena_gen += 1.0;
+    return 0;
+}
+
+void fx_peer_close_all(fx_ctx* ctx) {
+    for (int c = 0; c < fx_ctx::MAX_PEERS; ++c) {
+        if (ctx->peer_arena[c]) {
+            cudaIpcCloseMemHandle(ctx->peer_arena[c]);
+            cudaGetLastError();
+            ctx->peer_arena[c] = nullptr;
+        }
+        memset(ctx->peer_handle[c], 0, 64);
+        ctx->peer_gen[c] = 0.0;
+    }
+    ctx->peer_valid = false;
+}
+
+int fx_peer_exchange(fx_ctx* ctx, size_t off0, size_t off1) {
+    ctx->peer_valid = false;
+    const int G = ctx->world;
+    if (G <= 1 || G > fx_ctx::MAX_PEERS || !ctx->comm || ctx->peer_failed) return 0;
+    static const bool disabled = []() { const char* e = getenv("FXB200_NO_PEER"); return e && e[0] == '1'; }();
+    if (disabled) return 0;
+    constexpr int W = 12;                                  // doubles per rank in the exchange
+    cudaStream_t s = ctx->stream;
+    if (!ctx->peer_stage) FX_CUDA(cudaMalloc((void**)&ctx->peer_stage, (size_t)(W + W * fx_ctx::MAX_PEERS) * 8));
+    double* hp = ctx->pinned + 3072;                       // [W] send, then [G][W] received
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    double ok = 1.0;
+    if (!ctx->arena || cudaIpcGetMemHandle(&h, ctx->arena) != cudaSuccess) { cudaGetLastError(); ok = 0.0; }
+    else ctx->arena_exported = true;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(hp, &h, 64);
+    hp[8] = ok; hp[9] = ctx->arena_gen; hp[10] = (double)off0; hp[11] = (double)off1;
+    FX_CUDA(cudaMemcpyAsync(ctx->peer_stage, hp, W * 8, cudaMemcpyHostToDevice, s));
+    FX_TRY(fxcomm_allgather(ctx->comm, ctx->peer_stage, ctx->peer_stage + W, W, s));
+    FX_CUDA(cudaMemcpyAsync(hp + 16, ctx->peer_stage + W, (size_t)G * W * 8, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    bool all_ok = true, changed = false;
+    for (int c = 0; c < G; ++c) {
+        const double* r = hp + 16 + c * W;
+        if (r[8] != 1.0) all_ok = false;
+        if (memcmp(r, ctx->peer_handle[c], 64) != 0 || r[9] != ctx->peer_gen[c]) changed = true;
+        ctx->peer_off[c][0] = (size_t)r[10];
+        ctx->peer_off[c][1] = (size_t)r[11];
+    }
+    if (!all_ok) {                                         // same verdict on every rank
+        fx_peer_close_all(ctx);
+        ctx->peer_failed = true;
+        return 0;
+    }
+    if (changed) {
+        double fails = 0.0;
+        for (int c = 0; c < G; ++c) {
+            const double* r = hp + 16 + c * W;
+            const bool diff = memcmp(r, ctx->peer_handle[c], 64) != 0 || r[9] != ctx->peer_gen[c];
+            if (!diff) continue;
+            if (c != ctx->rank) {
+                if (ctx->peer_arena[c]) { cudaIpcCloseMemHandle(ctx->peer_arena[c]); cudaGetLastError(); ctx->peer_arena[c] = nullptr; }
+                cudaIpcMemHandle_t ph;
+                memcpy(&ph, r, 64);
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    fails += 1.0;
+                } else {
+                    ctx->peer_arena[c] = (char*)ptr;
+                }
+            }
+            memcpy(ctx->peer_handle[c], r, 64);
+            ctx->peer_gen[c] = r[9];
+        }
+        // every rank has dropped its stale mappings once this reduction completes
+        hp[0] = fails;
+        FX_CUDA(cudaMemcpyAsync(ctx->peer_stage, hp, 8, cudaMemcpyHostToDevice, s));
+        FX_TRY(fxcomm_allreduce_sum(ctx->comm, ctx->peer_stage, 1, s));
+        FX_CUDA(cudaMemcpyAsync(hp, ctx->peer_stage, 8, cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaStreamSynchronize(s));
+        for (char* a : ctx->retired) cudaFree(a);
+        ctx->retired.clear();
+        if (hp[0] != 0.0) {
+            fx_peer_close_all(ctx);
+            ctx->peer_failed = true;
+            return 0;
+        }
+    }
+    ctx->peer_valid = true;
     return 0;
 }
 
@@ -151,13 +244,18 @@ extern "C" int fx_ctx_info(const fx_ctx* ctx, int* device, int* rank, int* world
     return 0;
 }
 
+extern "C" int fx_ctx_peer_access(const fx_ctx* ctx) { return (ctx && ctx->peer_valid) ? 1 : 0; }
+
 extern "C" void fx_shutdown(fx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    fx_peer_close_all(ctx);
     if (ctx->comm) fxcomm_destroy(ctx->comm);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->arena) cudaFree(ctx->arena);
+    for (char* a : ctx->retired) cudaFree(a);
+    if (ctx->peer_stage) cudaFree(ctx->peer_stage);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

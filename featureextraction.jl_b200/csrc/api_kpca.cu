@@ -71,6 +71,15 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
         fx_set_error("internal: arena too small for the Gram stage");
         return FX_ERR_OOM;
     }
+    // Several ranks: map the peers' arenas so the Gram kernel can share out the symmetric blocks
+    // (gram.cu, sym = 2).  Collective; also orders this call after every rank's previous use of
+    // its K.  The offsets of K / rowpart inside each arena travel with the handles.
+    bool peer_sym = false;
+    if (ctx->world > 1 && variant == 0) {
+        FX_TRY(fx_peer_exchange(ctx, (size_t)((char*)g.K - ctx->arena),
+                                g.rowpart ? (size_t)((char*)g.rowpart - ctx->arena) : (size_t)0));
+        peer_sym = ctx->peer_valid;
+    }
     if (!x_dev && ctx->world > 1) {
         // Host input on several GPUs: every rank uploads only its own row block over PCIe and the
         // blocks are exchanged over NVLink (all ranks hitting the host with the full X at once is
@@ -110,10 +119,25 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
     ga.K = g.K; ga.ldk = g.n_ld; ga.rows_pad = g.ld; ga.rows_valid = g.rows_valid;
     ga.cols_valid = g.n; ga.diag_shift = g.row0; ga.rowpart = g.rowpart; ga.sym_source = 1;
     ga.kernel_id = kernel_id; ga.kp[0] = kp[0]; ga.kp[1] = kp[1]; ga.kp[2] = kp[2];
+    if (peer_sym) {
+        ga.peer_world = ctx->world; ga.peer_rank = ctx->rank;
+        for (int c = 0; c < ctx->world; ++c) {
+            if (c == ctx->rank) { ga.peerK[c] = g.K; ga.peerRowpart[c] = g.rowpart; continue; }
+            ga.peerK[c] = (double*)(ctx->peer_arena[c] + ctx->peer_off[c][0]);
+            ga.peerRowpart[c] = g.rowpart ? (double*)(ctx->peer_arena[c] + ctx->peer_off[c][1]) : nullptr;
+        }
+    }
     tm.begin(&st->gram_ms);
     FX_TRY(fx_launch_gram(ctx, ga, variant));
     tm.end();
     st->gram_launches++;
+    if (peer_sym) {
+        // the other ranks' mirrored tiles (and row-sum partials) must have landed in this rank's
+        // memory before anything reads K: kernel completion + a one-element reduction
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allreduce_sum(ctx->comm, g.scal + 8, 1, s));
+        tm.end();
+    }
 
     if (center) {
         // column sums == row sums (K symmetric): local rows, then all-gather

@@ -56,6 +56,19 @@ struct fx_ctx {
     // arena
     char* arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
+    // Peer mapping of the other ranks' arenas (CUDA IPC, one process per GPU on one node): the
+    // symmetric Gram kernel stores mirrored tiles straight into the owning rank's K over NVLink.
+    // Filled by fx_peer_exchange (collective); peer_valid says every peer arena is mapped.
+    static constexpr int MAX_PEERS = 16;
+    char* peer_arena[MAX_PEERS] = {};
+    unsigned char peer_handle[MAX_PEERS][64] = {};
+    double peer_gen[MAX_PEERS] = {};
+    size_t peer_off[MAX_PEERS][2] = {};          // per rank: arena offsets announced in the last exchange
+    bool peer_valid = false, peer_failed = false, arena_exported = false;
+    double arena_gen = 0.0;                      // bumped on every arena re-allocation
+    std::vector<char*> retired;                  // exported arenas replaced by a bigger one: freed once
+                                                 // every peer has dropped its mapping
+    double* peer_stage = nullptr;                // device staging for the handle all-gather
     // pinned scratch for small device->host reads inside solver loops
     double* pinned = nullptr;
     size_t pinned_cap = 0;
@@ -70,6 +83,13 @@ struct fx_ctx {
 int   fx_arena_reserve(fx_ctx* ctx, size_t bytes);
 void* fx_arena_alloc(fx_ctx* ctx, size_t bytes);
 static inline void fx_arena_reset(fx_ctx* ctx) { ctx->arena_off = 0; }
+// Collective over all ranks (no-op for world == 1): announces this rank's arena (IPC handle) and
+// the two arena offsets the caller wants peers to reach (K block, row-sum partials), maps every
+// peer's arena, and sets ctx->peer_valid.  Also a stream-ordered barrier across ranks.
+// Falls back to peer_valid == false (identically on every rank) if IPC is unavailable or
+// FXB200_NO_PEER=1.
+int fx_peer_exchange(fx_ctx* ctx, size_t off0, size_t off1);
+void fx_peer_close_all(fx_ctx* ctx);
 static inline size_t fx_align256(size_t b) { return (b + 255) & ~size_t(255); }
 
 // Event-pair timer accumulating into a double (resolved at the end of the call).

@@ -18,6 +18,14 @@ struct GramArgs {
     int kernel_id; double kp[3];
     int sym_source = 0;                 // 1: A is the row block [diag_shift, +rows_pad) of B (K symmetric)
     int no_symmetry = 0;                // 1: compute every tile even when the matrix is symmetric
+    // Cross-rank symmetry (sym_source only): with peer_world > 1 every rank launches the same
+    // call on its own row block; K / rowpart of rank c are reachable at peerK[c] / peerRowpart[c]
+    // (CUDA IPC mappings; the own entries are K / rowpart).  Each rank computes about half of its
+    // row block and stores the transposed tiles into the owning peer.  The caller provides the
+    // cross-rank barriers before (peer buffers free) and after (mirrored tiles landed).
+    int peer_world = 0, peer_rank = 0;
+    double* peerK[16] = {};
+    double* peerRowpart[16] = {};
 };
 int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, int64_t d_pad,
                        double* norms);

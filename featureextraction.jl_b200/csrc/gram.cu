@@ -12,15 +12,35 @@
 //   epilogue: kernel map applied IN REGISTERS (64 independent elements per thread, branch-free
 //     exp) --> row sums by 2-step warp shuffle --> 16-byte stores straight from the accumulator
 //     fragments (one store instruction covers 8 rows x 64 contiguous bytes = 16 full sectors).
+//
+// Symmetry.  K is symmetric when A is a row block of B.  sym = 1 (one rank, or no peer access):
+// inside this rank's square diagonal block only the tiles on / right of the diagonal are computed
+// and the strictly-right ones are mirrored by transposed stores from the fragments.  sym = 2
+// (several ranks, peer arenas mapped through CUDA IPC): the off-diagonal blocks are shared out
+// too -- of each pair of blocks (r,c) / (c,r) exactly one rank computes every 128x128 super-tile
+// and stores the transposed values, and the column sums that are the peer's row-sum partials,
+// STRAIGHT INTO THE PEER'S K over NVLink (plain st.global to the IPC-mapped address), so every
+// rank executes ~half of its row block and no separate exchange step exists.
 #include "fx_kernels.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3;
 constexpr int AS = BM + 4;                      // 132: (t*AS + g) mod 16 distinct for t,g in 0..3
 constexpr int BS = BN + 4;                      // 68
 constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25600 B)
-constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 2 * 2 * BM * 8 + 128;
+// mirror staging: per MMA warp two buffers of 8 transposed rows x 64 (+2 pad: conflict-free
+// 8-byte stores for lanes (g,t) -> word (2t+q)*TS + g) -- sent off with 512-byte bulk stores
+constexpr int TS = 66, TBUF_D = 8 * TS;
+constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 2 * 2 * BM * 8 + 128 + 4 * 2 * TBUF_D * 8;
+
+// 1-D bulk store shared -> global (TMA engine); the destination may be a peer GPU's memory
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                     __cvta_generic_to_global(dst_gmem)),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
 
 struct GramParams {
     const double* A; long lda;
@@ -31,23 +51,55 @@ struct GramParams {
     long rows_valid, cols_valid, diag_shift;
     int kt;
     int tiles_x, tiles_y; long tiles_total;
-    int sym;                          // 1: symmetric source (A == B): inside this rank's square diagonal
-                                      //    block compute only the tiles on / right of the diagonal and
-                                      //    mirror the strictly-right ones; other column blocks in full
+    int sym;                          // 0 / 1 / 2, see the header comment
+    int rank, world;                  // sym == 2: this rank's block index and the number of blocks
+    double* peerK[16];                // sym == 2: K of rank c (own entry = K)
+    double* peerRowpart[16];          //           rowpart of rank c (or null)
     KernelMap km;
 };
+
+// What this rank does with tile (ty, tx): 0 = skip (someone's mirror store produces it),
+// 1 = compute, 2 = compute and mirror into block `peer` (== own block inside the diagonal block).
+__device__ __forceinline__ int tile_role(const GramParams& p, int ty, int tx, int& peer) {
+    peer = p.rank;
+    if (!p.sym) return 1;
+    const int bw = 2 * p.tiles_y;                                 // tile-columns per rank block
+    const int c = (p.sym == 2) ? tx / bw : ((tx >= (int)(p.diag_shift / BN) && tx < (int)(p.diag_shift / BN) + bw) ? p.rank : -1);
+    if (c == p.rank) {
+        const int rel = tx - (int)(p.diag_shift / BN);
+        if (rel < 2 * ty) return 0;                               // left of the diagonal
+        return rel >= 2 * ty + 2 ? 2 : 1;
+    }
+    if (p.sym != 2) return 1;
+    const int delta = (c - p.rank + p.world) % p.world;
+    bool own;
+    if (2 * delta < p.world) own = true;
+    else if (2 * delta > p.world) own = false;
+    else own = (((ty + (tx - c * bw) / 2) & 1) == (p.rank < c ? 0 : 1));   // opposite blocks: checkerboard
+    peer = c;
+    return own ? 2 : 0;
+}
 
 // Tile order: column panels of PANEL tile-columns swept over all row blocks, so that the panel's
 // slab of the column operand (PANEL x 131 KB at d=256) stays L2-resident while the row operand
 // streams; a plain row-major sweep re-reads all of X from HBM once per row block.
+// sym == 2: the sweep goes rank block by rank block and starts at the rank's OWN block
+// (c = rank, rank+1, ... mod world), so that at any moment the ranks mirror into pairwise distinct
+// peers (a permutation over NVSwitch) instead of all into the same one.
 constexpr int PANEL = 128;
 __device__ __forceinline__ void tile_coords(const GramParams& p, long tile, long& i0, long& j0, int& tx) {
+    const int nblk = (p.sym == 2) ? p.world : 1;
+    const int bw = p.tiles_x / nblk;                           // tile-columns per block
+    const long per_block = (long)bw * p.tiles_y;
+    const int kb = (int)(tile / per_block);
+    const long inblk = tile - (long)kb * per_block;
     const long per_panel = (long)PANEL * p.tiles_y;
-    const int panel = (int)(tile / per_panel);
-    const long within = tile - (long)panel * per_panel;
-    const int pw = min(PANEL, p.tiles_x - panel * PANEL);      // last panel may be narrower
+    const int panel = (int)(inblk / per_panel);
+    const long within = inblk - (long)panel * per_panel;
+    const int pw = min(PANEL, bw - panel * PANEL);             // last panel of a block may be narrower
     const int ty = (int)(within / pw);
-    tx = panel * PANEL + (int)(within - (long)ty * pw);
+    const int blk = (p.sym == 2) ? (p.rank + kb) % p.world : 0;
+    tx = blk * bw + panel * PANEL + (int)(within - (long)ty * pw);
     i0 = (long)ty * BM;
     j0 = (long)tx * BN;
 }
@@ -56,22 +108,16 @@ __device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 1
 
 // Kernel map + row sums + stores for one warp's 64x32 accumulator tile.  EDGE tiles (ragged
 // borders or touching the diagonal) carry the validity masks and the same-point test; interior
-// tiles run the bare arithmetic.  MIRROR tiles (symmetric mode, strictly right of the diagonal
-// block) also write the transposed element K[j][i] (8 lanes x 8 B = 64 contiguous bytes per
-// column) and the column sums, which are the row-sum partials of the mirrored rows.
-template <int KID, bool EDGE, bool MIRROR>
-__device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[8][4][2],
-                                              const double (&ni)[8], const double (&nbv)[4][2], long i0,
-                                              long j0, int wm, int wn, int g, int t, double* rsb) {
+// tiles run the bare arithmetic.
+template <int KID, bool EDGE>
+__device__ __forceinline__ void gram_epilogue_plain(const GramParams& p, double (&acc)[8][4][2],
+                                                    const double (&ni)[8], const double (&nbv)[4][2], long i0,
+                                                    long j0, int wm, int wn, int g, int t, double* rsb) {
     const long jb = j0 + wn * 32 + 2 * t;
-    double csum[4][2];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) csum[nt][0] = csum[nt][1] = 0.0;
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) {
         const long i = i0 + wm * 64 + mt * 8 + g;
         double* krow = p.K + i * p.ldk + jb;
-        double* kcol = p.K + (jb - p.diag_shift) * p.ldk + i + p.diag_shift;   // transposed position of (i, jb)
         const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
         const bool iv = i < p.rows_valid;
         double sacc = 0.0;
@@ -89,12 +135,6 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
                 v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], false);
             }
             *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(v0, v1);
-            if (MIRROR) {
-                kcol[(long)(nt * 8) * p.ldk] = v0;
-                kcol[(long)(nt * 8 + 1) * p.ldk] = v1;
-                csum[nt][0] += v0;
-                csum[nt][1] += v1;
-            }
             sacc += v0 + v1;
         }
         if (p.rowpart) {
@@ -103,20 +143,103 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
             if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = sacc;
         }
     }
-    if (MIRROR && p.rowpart) {
-        // column sums over this warp's 64 rows = row-sum partial of mirrored row j for the 64-column
-        // slot [i0 + wm*64, +64) of that row: slot index = 2*(i0/BM) + wm
-        const long slot = p.diag_shift / BN + 2 * (i0 / BM) + wm;
+}
+
+// The same for MIRROR tiles (symmetric mode): also sends the transposed tile to its owner.
+template <int KID, bool EDGE>
+__device__ __forceinline__ void gram_epilogue_mirror(const GramParams& p, double (&acc)[8][4][2],
+                                              const double (&ni)[8], long i0,
+                                              long j0, int wm, int wn, int g, int t, double* rsb,
+                                              double* Kmir, double* rpmir, long mir_row0, double* tbuf) {
+    // Kmir / rpmir: K and rowpart of the rank that owns rows [mir_row0, +rows_pad) -- this rank
+    // itself inside the diagonal block, a peer (NVLink) for the shared-out blocks.  The mirrored
+    // values go through a small transposed staging buffer (tbuf: 2 x [8][TS] per warp) and leave
+    // as 512-byte bulk stores, 8 per 8-column group: direct transposed stores from the fragments
+    // are 64-byte pieces, which NVLink carries at a fraction of its bandwidth.
+    const long jb = j0 + wn * 32 + 2 * t;
+    const int lane = g * 4 + t;
+    double sacc[8];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+    for (int mt = 0; mt < 8; ++mt) sacc[mt] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                double v = csum[nt][q];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if (g == 0) p.rowpart[slot * p.rows_pad + (jb - p.diag_shift) + nt * 8 + q] = v;
+    for (int nt = 0; nt < 4; ++nt) {
+        double* tb = tbuf + (nt & 1) * TBUF_D;
+        double cs0 = 0.0, cs1 = 0.0;
+        // column norms re-read per group (L1 hit): keeps 12 registers free for the row sums
+        double nb0 = 0.0, nb1 = 0.0;
+        if (KID == 0) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(p.nb + jb + nt * 8));
+            nb0 = v.x; nb1 = v.y;
+        }
+        if (nt >= 2) {
+            // the bulk stores issued from this buffer two groups ago must have read it
+            if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+            const long i = i0 + wm * 64 + mt * 8 + g;
+            double v0, v1;
+            if (EDGE) {
+                const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+                const bool iv = i < p.rows_valid;
+                const long j = jb + nt * 8;
+                v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, ig == j);
+                v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, ig == j + 1);
+                v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
+                v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
+            } else {
+                v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, false);
+                v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, false);
             }
+            *reinterpret_cast<double2*>(p.K + i * p.ldk + jb + nt * 8) = make_double2(v0, v1);
+            {
+                tb[(2 * t) * TS + mt * 8 + g] = v0;
+                tb[(2 * t + 1) * TS + mt * 8 + g] = v1;
+                cs0 += v0;
+                cs1 += v1;
+            }
+            sacc[mt] += v0 + v1;
+        }
+        {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < 8) {
+                // transposed row j = j0 + wn*32 + nt*8 + lane, columns [i0 + wm*64, +64) of the owner's block
+                double* dst = Kmir + (j0 + wn * 32 + nt * 8 + lane - mir_row0) * p.ldk + i0 + wm * 64 + p.diag_shift;
+                bulk_s2g(dst, tb + lane * TS, 64 * 8);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (rpmir) {
+                // column sums over this warp's 64 rows = row-sum partial of mirrored row j for the
+                // 64-column slot [i0 + wm*64, +64) of that row: slot index = 2*(i0/BM) + wm
+                const long slot = p.diag_shift / BN + 2 * (i0 / BM) + wm;
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+                if (g == 0) {
+                    double* r = rpmir + slot * p.rows_pad + (jb - mir_row0) + nt * 8;
+                    *reinterpret_cast<double2*>(r) = make_double2(cs0, cs1);
+                }
+            }
+        }
+    }
+    {
+        // both staging buffers free again before the next tile touches them
+        if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+    }
+    if (p.rowpart) {
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+            double v = sacc[mt];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = v;
+        }
     }
 }
 
@@ -127,6 +250,7 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     double* rs = smem + (size_t)STAGES * STAGE_D;                  // [2 bufs][2 halves][BM]
     uint64_t* full = reinterpret_cast<uint64_t*>(rs + 4 * BM);
     uint64_t* empty = full + STAGES;
+    double* tstage = rs + 4 * BM + 16;                             // after the 128 bytes of mbarriers
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -147,10 +271,8 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
             tile_coords(p, tile, i0, j0, tx);
-            if (p.sym) {                                          // left of the diagonal inside the
-                const int rel = tx - (int)(p.diag_shift / BN);    // diagonal block: produced by a mirror store
-                if (rel >= 0 && rel < 2 * (int)(i0 / BM)) continue;
-            }
+            int peer;
+            if (tile_role(p, (int)(i0 / BM), tx, peer) == 0) continue;      // produced by a mirror store
             for (int kt = 0; kt < KT; ++kt, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);    // passes at once on first use
@@ -175,9 +297,10 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         long i0, j0; int tx;
         tile_coords(p, tile, i0, j0, tx);
-        const int rel = tx - (int)(p.diag_shift / BN);            // column tile relative to the diagonal block
-        if (p.sym && rel >= 0 && rel < 2 * (int)(i0 / BM)) continue;
-        const bool mirror = p.sym && rel >= 2 * (int)(i0 / BM) + 2 && rel < 2 * p.tiles_y;
+        int peer;
+        const int role = tile_role(p, (int)(i0 / BM), tx, peer);
+        if (role == 0) continue;
+        const bool mirror = role == 2;
         ++tcount;
         double acc[8][4][2];
 #pragma unroll
@@ -225,17 +348,21 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
                           (ig0 < j0 + BN && ig0 + BM > j0);
         if (mirror) {
-            if (edge) gram_epilogue<KID, true, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
-            else      gram_epilogue<KID, false, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+            double* Kmir = (p.sym == 2) ? p.peerK[peer] : p.K;
+            double* rpmir = (p.sym == 2) ? p.peerRowpart[peer] : p.rowpart;
+            const long mir_row0 = (p.sym == 2) ? (long)peer * p.rows_pad : p.diag_shift;
+            if (edge) gram_epilogue_mirror<KID, true>(p, acc, ni, i0, j0, wm, wn, g, t, rsb, Kmir, rpmir, mir_row0, tstage + warp * 2 * TBUF_D);
+            else      gram_epilogue_mirror<KID, false>(p, acc, ni, i0, j0, wm, wn, g, t, rsb, Kmir, rpmir, mir_row0, tstage + warp * 2 * TBUF_D);
         } else {
-            if (edge) gram_epilogue<KID, true, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
-            else      gram_epilogue<KID, false, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+            if (edge) gram_epilogue_plain<KID, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+            else      gram_epilogue_plain<KID, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
         }
         if (p.rowpart) {
             bar_sync_compute();                  // both column halves of every row are in smem
             p.rowpart[(long)tx * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
         }
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // mirrored tiles have left the SM
 }
 
 // ---- naive cross-check variant: one thread per output element -------------------------------
@@ -303,6 +430,18 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     // whole symmetric matrix on one rank: only tiles on / right of the diagonal block are computed
     p.sym = (a.sym_source && a.diag_shift >= 0 && a.diag_shift % BM == 0 &&
              a.diag_shift + a.rows_pad <= a.ldk && !a.no_symmetry) ? 1 : 0;
+    p.rank = 0; p.world = 1;
+    for (int c = 0; c < 16; ++c) { p.peerK[c] = nullptr; p.peerRowpart[c] = nullptr; }
+    if (p.sym && a.peer_world > 1) {
+        // cross-rank symmetry: needs every rank's block to be rows_pad wide and all peers mapped
+        if (a.peer_world > 16 || a.ldk != (int64_t)a.peer_world * a.rows_pad || a.diag_shift % a.rows_pad ||
+            a.peer_rank != (int)(a.diag_shift / a.rows_pad) || variant != 0) {
+            fx_set_error("gram: inconsistent peer layout (world %d, rank %d)", a.peer_world, a.peer_rank);
+            return FX_ERR_CUDA;
+        }
+        p.sym = 2; p.world = a.peer_world; p.rank = a.peer_rank;
+        for (int c = 0; c < a.peer_world; ++c) { p.peerK[c] = a.peerK[c]; p.peerRowpart[c] = a.peerRowpart[c]; }
+    }
     p.km.id = a.kernel_id; p.km.p0 = a.kp[0]; p.km.p1 = a.kp[1]; p.km.p2 = a.kp[2];
     double tmp[3];
     if (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp)) {

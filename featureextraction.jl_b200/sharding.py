@@ -29,3 +29,30 @@ def query_partition(m, world):
         out.append((q0, cnt))
         q0 += cnt
     return out
+
+
+def gram_tiles_executed(n, world, rank=0, peer=False):
+    """-> (executed, total): 128x64 output tiles of this rank's row block that the symmetric Gram
+    kernel actually computes (the rest arrive by mirror stores).  Restates tile_role() in
+    csrc/gram.cu: inside the rank's diagonal block only tiles on / right of the diagonal; with
+    ``peer`` (NVLink peer mappings) the off-diagonal blocks are shared out between the two ranks of
+    each pair as well (ring distance < world/2 owns; opposite blocks split in a checkerboard of
+    128x128 super-tiles)."""
+    import numpy as np
+    ld = row_partition(n, world)[0]
+    tiles_y, bw = ld // 128, 2 * (ld // 128)
+    ty = np.arange(tiles_y)[:, None]
+    executed = 0
+    for c in range(world):
+        rel = np.arange(bw)[None, :]
+        if c == rank:
+            executed += int((rel >= 2 * ty).sum())
+        elif not peer:
+            executed += tiles_y * bw
+        else:
+            delta = (c - rank) % world
+            if 2 * delta < world:
+                executed += tiles_y * bw
+            elif 2 * delta == world:
+                executed += int((((ty + rel // 2) & 1) == (0 if rank < c else 1)).sum())
+    return executed, tiles_y * bw * world

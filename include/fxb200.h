@@ -104,6 +104,10 @@ int  fx_comm_unique_id(void* id128);
 int  fx_init_distributed(int device, int rank, int world, const void* id128, fx_ctx** out);
 int  fx_set_stream(fx_ctx* ctx, void* cuda_stream);     /* run on a caller-owned stream    */
 int  fx_ctx_info(const fx_ctx* ctx, int* device, int* rank, int* world, int* sm_count);
+/* 1 if the last collective fit reached every other rank's workspace over NVLink peer mappings
+ * (CUDA IPC; symmetric blocks of K shared out between ranks), 0 if each rank computed its whole
+ * row block (one rank, peer access unavailable, or FXB200_NO_PEER=1).  Results are identical. */
+int  fx_ctx_peer_access(const fx_ctx* ctx);
 void fx_shutdown(fx_ctx* ctx);
 
 /* ---- KPCA ------------------------------------------------------------------------ */

@@ -50,8 +50,8 @@ def main():
             assert np.abs(T - To).max() <= 1e-10 * np.abs(To).max()
         model.free()
         if rank == 0:
-            print("DIST_GPU_OK world=%d n=%d k=%d steps=%d dense=%d comm_ms=%.3f angle=%.1e" %
-                  (world, n, k, st["steps"], st["dense_path"], st["comm_ms"], ang), flush=True)
+            print("DIST_GPU_OK world=%d n=%d k=%d steps=%d dense=%d comm_ms=%.3f angle=%.1e peer=%d" %
+                  (world, n, k, st["steps"], st["dense_path"], st["comm_ms"], ang, ctx.peer_access), flush=True)
     # KLDA on the same sharding (indicator K*V, class projector, CG all row-sharded)
     if len(args) < 3:
         n, d, c = 1500, 32, 5
