@@ -144,18 +144,19 @@ cudaEvent_t FxTimer::get_event() {
     }
     return ctx->ev_pool[ctx->ev_used++];
 }
-void FxTimer::begin(double* acc) {
+void FxTimer::begin(double* acc, cudaStream_t on) {
     Span sp;
     sp.a = get_event();
     sp.b = get_event();
     sp.acc = acc;
-    cudaEventRecord(sp.a, ctx->stream);
+    sp.s = on ? on : ctx->stream;
+    cudaEventRecord(sp.a, sp.s);
     open_.push_back((int)spans.size());
     spans.push_back(sp);
 }
 void FxTimer::end() {
     if (open_.empty()) return;
-    cudaEventRecord(spans[open_.back()].b, ctx->stream);
+    cudaEventRecord(spans[open_.back()].b, spans[open_.back()].s);
     open_.pop_back();
 }
 int FxTimer::resolve() {
@@ -194,6 +195,15 @@ static int ctx_common_init(int device, fx_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     FX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    {
+        // highest priority: its single-CTA kernels must get the first SM a K*V CTA vacates, not
+        // queue behind the rest of that grid
+        int least = 0, greatest = 0;
+        FX_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        FX_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, greatest));
+    }
+    FX_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    FX_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->pinned_cap = 4096;
     FX_CUDA(cudaMallocHost((void**)&c->pinned, c->pinned_cap * sizeof(double)));
     *out = c;
@@ -251,6 +261,9 @@ extern "C" void fx_shutdown(fx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     fx_peer_close_all(ctx);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->comm) fxcomm_destroy(ctx->comm);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->arena) cudaFree(ctx->arena);

@@ -52,6 +52,9 @@ struct fx_ctx {
     int device = 0, rank = 0, world = 1, sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    // side stream for the small Rayleigh-Ritz problem that runs beside the next K*V pass
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     FxComm* comm = nullptr;
     // arena
     char* arena = nullptr;
@@ -95,14 +98,14 @@ static inline size_t fx_align256(size_t b) { return (b + 255) & ~size_t(255); }
 // Event-pair timer accumulating into a double (resolved at the end of the call).
 struct FxTimer {
     fx_ctx* ctx;
-    struct Span { cudaEvent_t a, b; double* acc; };
+    struct Span { cudaEvent_t a, b; double* acc; cudaStream_t s; };
     std::vector<Span> spans;
     explicit FxTimer(fx_ctx* c) : ctx(c) {}
     ~FxTimer() { ctx->ev_used = 0; }
     cudaEvent_t get_event();
     std::vector<int> open_;       // stack of open spans (begin/end nest)
-    void begin(double* acc);      // records start on ctx->stream
-    void end();                   // records end for the innermost open span
+    void begin(double* acc, cudaStream_t on = nullptr);   // records start on `on` (default ctx->stream)
+    void end();                   // records end for the innermost open span, on the same stream
     int  resolve();               // after stream sync: adds elapsed ms to every accumulator
 };
 

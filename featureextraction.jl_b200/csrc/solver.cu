@@ -11,6 +11,7 @@
 // Multi-GPU: K, Q, W are row-sharded; per step one all-gather of the n x b block and a few
 // all-reduces of (m+b) x b / b x b matrices; the small dense work runs redundantly on every
 // rank from identical all-reduced inputs, so all ranks take identical decisions.
+#include <stdlib.h>
 #include "fx_kernels.cuh"
 
 void fx_resolve_opts(const fx_solver_opts* in, int k, fx_solver_opts* out) {
@@ -159,13 +160,11 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
 
     int m = 0, steps = 0, restarts = 0;
     bool converged = false;
-    double maxres = 0.0;
+    double maxres = 0.0, res_prev = -1.0, res_prev2 = -1.0;
     double* pinned = ctx->pinned;
-
-    while (true) {
-        double* Qn = w.Q + (size_t)m * ld;
-        const int mq = m + b;
-        // 1. gather the block, 2. W = K Qn
+    // One K*V pass: gather the block, W = K Qn.  The first pass of a fit with deferred centring
+    // also centres K in place (symm.cu CENTER variant) and is booked as the centring pass.
+    auto kv_pass = [&](const double* Qn, bool first) -> int {
         const double* Vsrc = Qn;
         if (ctx->world > 1) {
             tm.begin(&st->comm_ms);
@@ -177,9 +176,7 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
         sa.K = a.K; sa.ldk = a.ldk; sa.rows_pad = ld; sa.V = Vsrc; sa.ldr = ld;
         sa.v_rank_stride = (int64_t)b * ld; sa.bcols = b; sa.Y = w.Wa; sa.Ypart = w.Ypart;
         sa.splits = w.splits;
-        if (steps == 0 && a.center_colmean) {
-            // deferred centring: this pass centres K in place while it multiplies (one read of K
-            // serves both); it is booked as the centring pass
+        if (first && a.center_colmean) {
             sa.center_colmean = a.center_colmean; sa.center_grand = a.center_grand;
             sa.rows_valid = a.rows_valid; sa.cols_valid = a.n; sa.row0 = a.row0;
             tm.begin(&st->center_ms);
@@ -192,6 +189,22 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
             tm.end();
             st->symm_launches++;
         }
+        return 0;
+    };
+    // The Rayleigh-Ritz problem of step s (single-CTA Jacobi, latency bound) runs on the side
+    // stream while the main stream already computes K*Qn for step s+1: that product does not
+    // depend on the Ritz pairs (only the convergence decision and a thick restart do).  When the
+    // residual history says step s probably converges, the solver does not run ahead, so the
+    // speculative pass is wasted at most when the prediction fails.
+    static const bool overlap_off = []() { const char* e = getenv("FXB200_NO_OVERLAP"); return e && e[0] == '1'; }();
+    bool pending = false;                               // W = K*Qn for this step is already in Wa
+    int wasted = 0;
+
+    while (true) {
+        double* Qn = w.Q + (size_t)m * ld;
+        const int mq = m + b;
+        if (!pending) FX_TRY(kv_pass(Qn, steps == 0));
+        pending = false;
         steps++;
         // 3-5. CGS2 against [Q Qn]; H accumulates both passes
         FX_TRY(project_out(ctx, w, mq, w.Wa, ld, w.H, variant, tm, st));
@@ -205,16 +218,37 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
         FX_TRY(svqb_pass(ctx, w, w.Wb, w.Q + (size_t)mq * ld, ld, w.M2, w.C2, variant, tm, st));
         FX_TRY(fx_launch_small_matmul(ctx, w.C2, w.C1, b, w.C));
         m = mq;
-        // 8. Rayleigh-Ritz
-        tm.begin(&st->rr_ms);
-        FX_TRY(fx_launch_copy2d(ctx, w.T, mt, w.Tw, mt, m, m));
-        FX_TRY(fx_launch_jacobi(ctx, w.Tw, mt, m, w.S, mt, w.theta, w.Jw, w.info));
-        FX_TRY(fx_launch_ritz_residuals(ctx, w.C, b, w.S, mt, m, k, w.res));
-        tm.end();
-        FX_CUDA(cudaMemcpyAsync(pinned, w.res, k * sizeof(double), cudaMemcpyDeviceToHost, s));
-        FX_CUDA(cudaMemcpyAsync(pinned + 64, w.theta, sizeof(double), cudaMemcpyDeviceToHost, s));
-        FX_CUDA(cudaMemcpyAsync(pinned + 72, w.info, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
-        FX_CUDA(cudaStreamSynchronize(s));
+        // 8. Rayleigh-Ritz on the side stream
+        FX_CUDA(cudaEventRecord(ctx->ev_fork, s));
+        FX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        {
+            cudaStream_t keep = ctx->stream;
+            ctx->stream = ctx->side;                    // the launchers below use ctx->stream
+            tm.begin(&st->rr_ms);
+            int rc = fx_launch_copy2d(ctx, w.T, mt, w.Tw, mt, m, m);
+            if (!rc) rc = fx_launch_jacobi(ctx, w.Tw, mt, m, w.S, mt, w.theta, w.Jw, w.info);
+            if (!rc) rc = fx_launch_ritz_residuals(ctx, w.C, b, w.S, mt, m, k, w.res);
+            tm.end();
+            ctx->stream = keep;
+            FX_TRY(rc);
+        }
+        FX_CUDA(cudaMemcpyAsync(pinned, w.res, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->side));
+        FX_CUDA(cudaMemcpyAsync(pinned + 64, w.theta, sizeof(double), cudaMemcpyDeviceToHost, ctx->side));
+        FX_CUDA(cudaMemcpyAsync(pinned + 72, w.info, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->side));
+        FX_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+        // run ahead with the next K*V pass unless this step is expected to converge
+        bool likely_done = false;
+        if (res_prev >= 0.0 && res_prev2 > 0.0) {
+            double ratio = res_prev / res_prev2;
+            if (ratio > 1.0) ratio = 1.0;
+            likely_done = res_prev * ratio <= 100.0 * o.tol;
+        }
+        if (!overlap_off && variant == 0 && steps < o.max_steps && !likely_done) {
+            FX_TRY(kv_pass(w.Q + (size_t)m * ld, false));
+            pending = true;
+        }
+        FX_CUDA(cudaEventSynchronize(ctx->ev_join));
+        FX_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));      // T, S, theta are free for the main stream again
         const double scale = fabs(pinned[64]) > 1e-300 ? fabs(pinned[64]) : 1e-300;
         maxres = 0.0;
         bool finite = true;
@@ -227,8 +261,13 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
             fx_set_error("eigensolver: non-finite Ritz residual at step %d", steps);
             return FX_ERR_NOT_CONVERGED;
         }
+        res_prev2 = res_prev;
+        res_prev = maxres;
         converged = maxres <= o.tol;
-        if (converged || steps >= o.max_steps) break;
+        if (converged || steps >= o.max_steps) {
+            if (pending) wasted = 1;
+            break;
+        }
         if (m + b > w.mcap) {
             // thick restart: keep the b leading Ritz vectors, T = diag(theta)
             tm.begin(&st->ortho_ms);
@@ -242,6 +281,7 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
             restarts++;
         }
     }
+    steps += wasted;                                    // K*V passes actually executed
     st->steps = steps;
     st->restarts = restarts;
     st->converged = converged ? 1 : 0;
