@@ -1,5 +1,6 @@
 // api_kpca.cu -- C ABI: KPCA fit (kpca, /root/reference/src/kpca.jl:49-57) and the exposed
 // building blocks (Gram, centring, K*V, small eigensolver).
+#include <stdlib.h>
 #include "fx_kernels.cuh"
 #include <math.h>
 
@@ -233,9 +234,16 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     const int64_t ld = round_up(ceil_div(n, G), 128), n_ld = ld * G;
     if (!opts || opts->max_blocks <= 1) {
         // basis depth: a deeper basis saves K*V passes but makes every Rayleigh-Ritz (device
-        // Jacobi, ~m^3) dearer; keep 5 blocks while a pass over this rank's K costs > 2 ms
+        // Jacobi, ~m^3, single CTA) dearer.  The Rayleigh-Ritz runs beside the next pass, so it is
+        // free while it is shorter than a solver step: 5 blocks while a pass over this rank's K
+        // costs > 2 ms, 4 down to 0.3 ms (measured on 8 GPUs at n = 65536: 18.1 / 17.5 / 18.5 ms
+        // per fit with 3 / 4 / 5), 3 below that
         const double pass_ms = 8.0 * (double)ld * (double)n_ld / 6.5e9;
-        o.max_blocks = pass_ms > 2.0 ? 5 : 3;
+        o.max_blocks = pass_ms > 2.0 ? 5 : (pass_ms > 0.3 ? 4 : 3);
+        if (const char* e = getenv("FXB200_MAX_BLOCKS")) {        // tuning knob for experiments
+            const int v = atoi(e);
+            if (v >= 2 && v <= 8) o.max_blocks = v;
+        }
     }
     const int64_t row0 = ld * ctx->rank;
     int64_t rows_valid = n - row0;

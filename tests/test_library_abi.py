@@ -69,3 +69,30 @@ def test_sharding_rules():
     assert sum(c for _, c in query_partition(1000003, 8)) == 1000003
     with pytest.raises(ValueError):
         row_partition(0, 2)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("peer", [False, True])
+def test_symmetric_gram_tile_ownership_covers_every_tile_once(world, peer):
+    """The ownership rule of the symmetric Gram kernel (csrc/gram.cu tile_role, restated in
+    sharding.gram_tile_roles): over all ranks every 64x64 cell of the global matrix is produced
+    exactly once, either by the tile that computes it or by exactly one mirror store."""
+    import numpy as np
+    n = 128 * 3 * world - 5
+    ld = fxb200.sharding.row_partition(n, world)[0]
+    ty_n = ld // 128
+    cells = np.zeros((2 * ty_n * world, 2 * ty_n * world), dtype=np.int64)   # 64x64 cells
+    for r in range(world):
+        role, target = fxb200.sharding.gram_tile_roles(n, world, r, peer)
+        for ty in range(role.shape[0]):
+            for tx in range(role.shape[1]):
+                if role[ty, tx] == 0:
+                    continue
+                gi = 2 * (r * ty_n + ty)                     # first 64-row cell of the 128-row tile
+                cells[gi:gi + 2, tx] += 1
+                if role[ty, tx] == 2:                        # transposed: 64 rows x 128 columns
+                    assert peer or target[ty, tx] == r
+                    cells[tx, gi:gi + 2] += 1
+    assert (cells == 1).all()
+    ex = [fxb200.sharding.gram_tiles_executed(n, world, r, peer)[0] for r in range(world)]
+    assert max(ex) - min(ex) <= ty_n                      # balanced across ranks

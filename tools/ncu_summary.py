@@ -27,7 +27,13 @@ for h, u, v in zip(rr[0], rr[1], rr[2]):
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 if len(rows) > 3:
-    hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}; data = rows[2:]
+    hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
+    # a report with several kernels repeats the header block per kernel: keep the first kernel only
+    data = []
+    for r in rows[2:]:
+        if len(r) < len(hdr) or r == hdr:
+            break
+        data.append(r)
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     dm = [i for i, r in enumerate(data) if "DMMA" in r[ix["Source"]]]
     spans = {"all": (0, len(data))}
