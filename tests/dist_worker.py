@@ -38,6 +38,39 @@ class GlooOps:
         return np.concatenate([o.numpy() for o in outs], axis=0)
 
 
+def peer_symmetric_gram(kern, X, n, world, rank):
+    """The cross-rank symmetric Gram of csrc/gram.cu (sym = 2) with the peer stores emulated by an
+    all-reduce: every rank computes only the 128x64 tiles sharding.gram_tile_roles gives it and
+    'stores' each mirrored tile transposed into the owning rank's rows; the column sums of a
+    mirrored tile are the owner's row-sum partials.  Returns this rank's padded row block
+    [ld][n_ld] and its row sums [ld]; asserts every element was written exactly once."""
+    from fxb200.sharding import gram_tile_roles
+    ld, n_ld, parts = row_partition(n, world)
+    Xp = np.zeros((n_ld, X.shape[1])); Xp[:n] = X
+    valid = np.arange(n_ld) < n
+    role, target = gram_tile_roles(n, world, rank, peer=True)
+    writes = np.zeros((n_ld, n_ld)); count = np.zeros((n_ld, n_ld)); rsum = np.zeros(n_ld)
+    r0 = rank * ld
+    for ty in range(role.shape[0]):
+        for tx in range(role.shape[1]):
+            if role[ty, tx] == 0:
+                continue
+            gi, gj = r0 + 128 * ty, 64 * tx
+            tile = O.kernelmatrix(kern, Xp[gi:gi + 128], Xp[gj:gj + 64])
+            tile = tile * valid[gi:gi + 128, None] * valid[None, gj:gj + 64]     # padding written as 0
+            writes[gi:gi + 128, gj:gj + 64] += tile; count[gi:gi + 128, gj:gj + 64] += 1
+            rsum[gi:gi + 128] += tile.sum(axis=1)
+            if role[ty, tx] == 2:
+                assert gj // ld == target[ty, tx]
+                writes[gj:gj + 64, gi:gi + 128] += tile.T; count[gj:gj + 64, gi:gi + 128] += 1
+                rsum[gj:gj + 64] += tile.sum(axis=0)
+    for a in (writes, count, rsum):
+        t = torch.from_numpy(a)
+        dist.all_reduce(t)
+    assert (count == 1).all(), "a tile was produced %s times" % np.unique(count)
+    return writes[r0:r0 + ld], rsum[r0:r0 + ld]
+
+
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -53,6 +86,11 @@ def main():
     row0, rows = parts[rank]
     # each rank builds only its row block of K (Gram shards by rows, no collective)
     Kloc = O.kernelmatrix(kern, X[row0:row0 + rows], X)          # rows x n
+    # the same block through the cross-rank symmetric ownership (mirrored tiles 'stored' into peers)
+    Ksym, rs_sym = peer_symmetric_gram(kern, X, n, world, rank)
+    assert np.array_equal(Ksym[rows:], np.zeros((ld - rows, n_ld))) and not Ksym[:, n:].any()
+    np.testing.assert_allclose(Ksym[:rows, :n], Kloc, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(rs_sym[:rows], Kloc.sum(axis=1), rtol=1e-13)
     # centring: local row sums, all-gather, then the local update
     rs = np.zeros(ld); rs[:rows] = Kloc.sum(axis=1)
     outs = [torch.zeros(ld, dtype=torch.float64) for _ in range(world)]
