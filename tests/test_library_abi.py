@@ -96,3 +96,77 @@ def test_symmetric_gram_tile_ownership_covers_every_tile_once(world, peer):
     assert (cells == 1).all()
     ex = [fxb200.sharding.gram_tiles_executed(n, world, r, peer)[0] for r in range(world)]
     assert max(ex) - min(ex) <= ty_n                      # balanced across ranks
+
+
+def _header_prototypes():
+    """name -> (return class, [argument classes]) parsed from include/fxb200.h;
+    classes: 'int', 'i64', 'f64', 'ptr', 'void', 'cstr'."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+
+    def cls(t):
+        t = t.strip()
+        if "*" in t:
+            return "cstr" if re.match(r"const\s+char\s*\*", t) else "ptr"
+        base = re.sub(r"\bconst\b", "", t).split()
+        if not base:
+            return "void"
+        # drop the parameter name if present
+        ty = base[0] if len(base) == 1 else " ".join(base[:-1])
+        return {"int": "int", "int32_t": "int", "int64_t": "i64", "double": "f64", "void": "void",
+                "uint64_t": "i64", "size_t": "i64"}[ty]
+
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(fx_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        argl = [] if args.strip() in ("", "void") else [cls(a) for a in args.split(",")]
+        protos[name] = (cls(ret + " x") if "*" not in ret else cls(ret), argl)
+    return protos
+
+
+def test_julia_wrapper_ccalls_match_header():
+    """Julia is not in the image, so the wrapper cannot be executed here: check statically that
+    every ccall names a declared symbol and passes the declared number and kinds of arguments."""
+    protos = _header_prototypes()
+    src = open(os.path.join(ROOT, "julia", "FeatureExtractionB200.jl")).read()
+    jl = {"Cint": "int", "Int64": "i64", "Float64": "f64", "Cvoid": "void", "Cstring": "cstr"}
+    calls = list(re.finditer(r"ccall\(\(:(fx_[a-z0-9_]+),\s*libfx\),\s*(\w+),\s*\(", src))
+    assert len(calls) >= 10
+    seen = set()
+    for m in calls:
+        name, ret = m.group(1), m.group(2)
+        # argument type tuple: balanced parentheses from the '(' that ends the match
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        tup = src[m.end():i - 1]
+        parts = [p.strip() for p in re.split(r",(?![^{}]*\})", tup) if p.strip()]
+        kinds = ["ptr" if p.startswith(("Ptr{", "Ref{")) else jl[p] for p in parts]
+        assert name in protos, "ccall of undeclared symbol %s" % name
+        hret, hargs = protos[name]
+        assert jl[ret] == hret, (name, ret, hret)
+        assert kinds == hargs, "%s: Julia passes %s, header declares %s" % (name, kinds, hargs)
+        seen.add(name)
+    for required in ("fx_init", "fx_shutdown", "fx_kpca_fit_f64", "fx_kpca_transform_f64", "fx_klda_fit_f64",
+                     "fx_model_create_f64", "fx_model_free", "fx_pca_f64", "fx_lda_f64", "fx_project_f64"):
+        assert required in seen, required
+
+
+def test_ctypes_prototypes_match_header():
+    """The ctypes argument lists have the header's arity and pointer / scalar kinds."""
+    protos = _header_prototypes()
+    kind = {ctypes.c_int: "int", ctypes.c_int32: "int", ctypes.c_int64: "i64", ctypes.c_double: "f64",
+            ctypes.c_uint64: "i64", ctypes.c_size_t: "i64"}
+    for name, (restype, argtypes) in fxb200.PROTOTYPES.items():
+        assert name in protos, name
+        hret, hargs = protos[name]
+        got = [kind.get(a, "ptr") for a in argtypes]
+        assert got == hargs, "%s: ctypes %s vs header %s" % (name, got, hargs)
+        if restype is None:
+            assert hret == "void", name
+        elif restype is ctypes.c_char_p:
+            assert hret == "cstr", name
+        else:
+            assert kind.get(restype, "ptr") == hret, name
