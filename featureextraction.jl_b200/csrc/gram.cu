@@ -4,7 +4,7 @@
 //
 // Data path (persistent CTAs, 2 per SM, each looping over 128x64 output tiles):
 //   producer warpgroup (one active warp; gives its registers to the MMA warps via setmaxnreg):
-//     HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 4-stage smem ring of
+//     HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 3-stage smem ring of
 //     16-feature slabs; it runs ahead across tile boundaries, so the next tile's first slabs
 //     land while the MMA warps are still in the epilogue of the previous one
 //   4 MMA warps: LDS.64 conflict-free (row stride = 4 mod 16 doubles) --> DMMA.8x8x4

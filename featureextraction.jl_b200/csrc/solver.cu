@@ -1,7 +1,8 @@
 // solver.cu -- top-k symmetric eigensolve on the device: thick-restart block Krylov
 // (Krylov-Schur form) whose only heavy operation is Y = K V (symm.cu), with full CGS2
-// re-orthogonalisation on DMMA tall-skinny kernels (tsgemm.cu), SVQB block orthonormalisation
-// and Rayleigh-Ritz by a device Jacobi solver (smalldense.cu).
+// re-orthogonalisation on DMMA tall-skinny kernels (tsgemm.cu), CholQR / SVQB block
+// orthonormalisation and Rayleigh-Ritz by a device Jacobi solver (smalldense.cu) that runs on a
+// side stream beside the next K V pass.
 //
 // Replaces components_eig! -> syevd! -> ccall dsyevd_ (/root/reference/src/common.jl:161-165,
 // :107-143, :128-131), which computes ALL n eigenpairs in O(n^3); the caller of kpca

@@ -57,7 +57,7 @@ enum { FX_OK = 0, FX_ERR_CUDA = 1, FX_ERR_NCCL = 2, FX_ERR_OOM = 3,
 /* Eigensolver / CG options.  Zero in any field selects the default. */
 typedef struct fx_solver_opts {
     int32_t block;        /* Krylov block width b (default: k rounded up to 8, max 64)      */
-    int32_t max_blocks;   /* basis capacity in blocks before a thick restart (default 5 or 3) */
+    int32_t max_blocks;   /* basis capacity in blocks before a thick restart (0: 5, 4 or 3 by K size) */
     int32_t max_steps;    /* K*V passes allowed (default 300)                                */
     int32_t variant;      /* 0 = tuned kernels, 1 = naive CUDA kernels (debug cross-check)   */
     double  tol;          /* Ritz residual tolerance relative to |theta_1| (default 1e-12)   */
