@@ -193,12 +193,10 @@ __device__ __forceinline__ void gram_epilogue_mirror(const GramParams& p, double
                 v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, false);
             }
             *reinterpret_cast<double2*>(p.K + i * p.ldk + jb + nt * 8) = make_double2(v0, v1);
-            {
-                tb[(2 * t) * TS + mt * 8 + g] = v0;
-                tb[(2 * t + 1) * TS + mt * 8 + g] = v1;
-                cs0 += v0;
-                cs1 += v1;
-            }
+            tb[(2 * t) * TS + mt * 8 + g] = v0;              // transposed: row = column of the tile
+            tb[(2 * t + 1) * TS + mt * 8 + g] = v1;
+            cs0 += v0;
+            cs1 += v1;
             sacc[mt] += v0 + v1;
         }
         {
