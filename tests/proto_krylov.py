@@ -36,12 +36,34 @@ def hash_uniform(rows, cols, seed):
     return (z >> np.uint64(11)).astype(np.float64) * (2.0 ** -52) - 1.0
 
 
-def svqb(W, ops, tol=1e-14):
-    """One SVQB pass: G = W'W, scale by diag, eigendecompose, W <- W D^-1/2 U L^-1/2.
-    Returns (W_orth, Cfac, ndef) with W_old = W_orth @ Cfac."""
+def chol_factors(Gs, thr):
+    """Right-looking Cholesky of the scaled Gram matrix as chol_factors_kernel (smalldense.cu)
+    does it: returns lower L with Gs = L L', or None as soon as a pivot is <= thr."""
+    b = Gs.shape[0]
+    L = np.tril(0.5 * (Gs + Gs.T))
+    for j in range(b):
+        piv = L[j, j]
+        if not piv > thr:
+            return None
+        L[j:, j] /= np.sqrt(piv)
+        for c in range(j + 1, b):
+            L[c:, c] -= L[c:, j] * L[c, j]
+    return L
+
+
+def svqb(W, ops, tol=1e-14, chol_thr=1e-8):
+    """One block orthonormalisation pass: G = W'W scaled by its diagonal; CholQR when every
+    pivot of the Cholesky exceeds chol_thr (W_orth = W D^-1 L^-T), else SVQB: eigendecompose,
+    W <- W D^-1/2 U L^-1/2.  Returns (W_orth, Cfac, ndef) with W_old = W_orth @ Cfac."""
     G = ops.allreduce(W.T @ W)
     d = np.sqrt(np.maximum(np.diag(G), 1e-300))
     Gs = G / d[:, None] / d[None, :]
+    L = chol_factors(Gs, chol_thr) if chol_thr is not None else None
+    if L is not None:
+        Li = np.linalg.inv(L)
+        M = Li.T / d[:, None]                             # W_orth = W M
+        Cfac = L.T * d[None, :]                           # W = W_orth Cfac
+        return W @ M, Cfac, 0
     lam, U = np.linalg.eigh(Gs)
     lmax = lam.max()
     ndef = int((lam < tol * lmax).sum())
