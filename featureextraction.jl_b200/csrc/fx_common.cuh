@@ -196,15 +196,32 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Branch-free exp(x) for x <= 0 (the Gaussian kernel's argument), 13 FP64-pipe operations:
 // x = (64 m + j) ln2/64 + r with |r| <= ln2/128 (Cody-Waite, hi/lo), exp(x) = 2^m * T[j] * e^r,
 // T[j] = 2^(j/64) as a hi+lo pair (one 16-byte load), e^r - 1 by a degree-5 polynomial
-// (truncation 3.5e-17).  Measured max error 0.65 ulp over [-700, 0]; exact 1 at x = 0; results
-// x < -708 are clamped (result 2.4e-308 instead of a subnormal / 0: absolute error < 2.3e-308).
+// (truncation 3.5e-17).  Max error 0.83 ulp against 80-bit expl() over [-708, 0] (measured on the host
+// build of this very function, tests/test_device_math_host.py); exact 1 at x = 0; results
+// x < -708 are clamped (result exp(-708) = 3.3e-308 instead of a subnormal / 0: absolute error < 3.4e-308).
 // Small positive x (cancellation in ||x||^2+||y||^2-2x'y) are fine.  DMMA and DFMA share one FP64
 // datapath on B200, so every operation saved here is DMMA issue time.
-static __device__ const double fx_exp_tab[128] = {1.0, 0.0, 1.0108892860517005, -1.5234778603368577e-17, 1.0218971486541166, 5.109225028973444e-17, 1.0330248790212284, 7.600838874027088e-18, 1.0442737824274138, 8.551889705537965e-17, 1.0556451783605572, 1.759325738772092e-18, 1.0671404006768237, -7.899853966841582e-17, 1.0787607977571199, -6.656660436056593e-17, 1.0905077326652577, -3.046782079812471e-17, 1.102382583307841, 5.2660368715706944e-17, 1.1143867425958924, 1.0410278456845571e-16, 1.1265216186082418, 5.165856758795457e-17, 1.1387886347566916, 8.912812676025408e-17, 1.1511892299529827, 3.250710218863827e-17, 1.1637248587775775, 3.8292048369240935e-17, 1.1763969916502812, 5.554203254218079e-17, 1.189207115002721, 3.982015231465646e-17, 1.202156731452703, 6.644981499252301e-17, 1.215247359980469, -7.712630692681488e-17, 1.22848053610687, -1.89878163130253e-17, 1.241857812073484, 4.658027591836937e-17, 1.255380757024691, -6.7113898212968784e-18, 1.2690509571917332, 2.667932131342186e-18, 1.2828700160787783, 1.713594918243561e-17, 1.2968395546510096, 2.5382502794888315e-17, 1.3109612115247644, -7.181536135519454e-17, 1.3252366431597413, -2.8587312100388614e-17, 1.339667524053303, 8.927282594831732e-17, 1.3542555469368927, 7.70094837980299e-17, 1.3690024229745905, 9.593797919118849e-17, 1.383909881963832, -6.770511658794786e-17, 1.3989796725383112, -9.614213209051323e-17, 1.4142135623730951, -9.667293313452913e-17, 1.42961333839197, -1.2031642489053655e-17, 1.4451808069770467, -3.0237581349939873e-17, 1.460917794180647, -5.600377186075216e-17, 1.4768261459394993, -3.483994556892796e-17, 1.4929077282912648, 1.4192920154284036e-17, 1.5091644275934228, -1.016455327754295e-16, 1.5255981507445384, -1.1024941712342561e-16, 1.5422108254079407, 7.949834809697621e-17, 1.559004400237837, 3.7812070533575275e-17, 1.5759808451078865, -1.0136916471278304e-17, 1.593142151342267, -1.0094406542311964e-16, 1.6104903319492543, 2.4707192569797888e-17, 1.6280274218573478, -6.712955084707084e-17, 1.645755478153965, -1.0125679913674773e-16, 1.6636765803267364, 5.8909926967131e-17, 1.681792830507429, 8.199010020581497e-17, 1.7001063537185235, -8.0237193703977e-18, 1.718619298122478, -1.851380418263111e-17, 1.7373338352737062, 3.164389299292957e-17, 1.7562521603732995, 2.960140695448873e-17, 1.7753764925265212, 6.429731796556572e-17, 1.7947090750031072, 1.8227458427912087e-17, 1.8142521755003989, -9.969531538920349e-17, 1.8340080864093424, 3.283107224245627e-17, 1.8539791250833855, 9.761887490727594e-17, 1.8741676341103, -6.122763413004143e-17, 1.8945759815869656, 3.4034035352165297e-17, 1.9152065613971474, -1.0619946056195963e-16, 1.9360617934922943, 1.0332385960676326e-16, 1.9571441241754002, 8.960767791036668e-17, 1.978456026387951, 4.0388753109278167e-17};
-__device__ __forceinline__ double fx_exp_nonpos(double x) {
+#define FX_EXP_TAB_VALUES 1.0, 0.0, 1.0108892860517005, -1.5234778603368577e-17, 1.0218971486541166, 5.109225028973444e-17, 1.0330248790212284, 7.600838874027088e-18, 1.0442737824274138, 8.551889705537965e-17, 1.0556451783605572, 1.759325738772092e-18, 1.0671404006768237, -7.899853966841582e-17, 1.0787607977571199, -6.656660436056593e-17, 1.0905077326652577, -3.046782079812471e-17, 1.102382583307841, 5.2660368715706944e-17, 1.1143867425958924, 1.0410278456845571e-16, 1.1265216186082418, 5.165856758795457e-17, 1.1387886347566916, 8.912812676025408e-17, 1.1511892299529827, 3.250710218863827e-17, 1.1637248587775775, 3.8292048369240935e-17, 1.1763969916502812, 5.554203254218079e-17, 1.189207115002721, 3.982015231465646e-17, 1.202156731452703, 6.644981499252301e-17, 1.215247359980469, -7.712630692681488e-17, 1.22848053610687, -1.89878163130253e-17, 1.241857812073484, 4.658027591836937e-17, 1.255380757024691, -6.7113898212968784e-18, 1.2690509571917332, 2.667932131342186e-18, 1.2828700160787783, 1.713594918243561e-17, 1.2968395546510096, 2.5382502794888315e-17, 1.3109612115247644, -7.181536135519454e-17, 1.3252366431597413, -2.8587312100388614e-17, 1.339667524053303, 8.927282594831732e-17, 1.3542555469368927, 7.70094837980299e-17, 1.3690024229745905, 9.593797919118849e-17, 1.383909881963832, -6.770511658794786e-17, 1.3989796725383112, -9.614213209051323e-17, 1.4142135623730951, -9.667293313452913e-17, 1.42961333839197, -1.2031642489053655e-17, 1.4451808069770467, -3.0237581349939873e-17, 1.460917794180647, -5.600377186075216e-17, 1.4768261459394993, -3.483994556892796e-17, 1.4929077282912648, 1.4192920154284036e-17, 1.5091644275934228, -1.016455327754295e-16, 1.5255981507445384, -1.1024941712342561e-16, 1.5422108254079407, 7.949834809697621e-17, 1.559004400237837, 3.7812070533575275e-17, 1.5759808451078865, -1.0136916471278304e-17, 1.593142151342267, -1.0094406542311964e-16, 1.6104903319492543, 2.4707192569797888e-17, 1.6280274218573478, -6.712955084707084e-17, 1.645755478153965, -1.0125679913674773e-16, 1.6636765803267364, 5.8909926967131e-17, 1.681792830507429, 8.199010020581497e-17, 1.7001063537185235, -8.0237193703977e-18, 1.718619298122478, -1.851380418263111e-17, 1.7373338352737062, 3.164389299292957e-17, 1.7562521603732995, 2.960140695448873e-17, 1.7753764925265212, 6.429731796556572e-17, 1.7947090750031072, 1.8227458427912087e-17, 1.8142521755003989, -9.969531538920349e-17, 1.8340080864093424, 3.283107224245627e-17, 1.8539791250833855, 9.761887490727594e-17, 1.8741676341103, -6.122763413004143e-17, 1.8945759815869656, 3.4034035352165297e-17, 1.9152065613971474, -1.0619946056195963e-16, 1.9360617934922943, 1.0332385960676326e-16, 1.9571441241754002, 8.960767791036668e-17, 1.978456026387951, 4.0388753109278167e-17
+static __device__ const double fx_exp_tab[128] = {FX_EXP_TAB_VALUES};
+// Host mirror of the table and of the three bit-level intrinsics so that fx_exp_nonpos also
+// compiles for the host (tests/test_device_math_host.py measures its error against expl()).
+#ifndef __CUDA_ARCH__
+static const double fx_exp_tab_host[128] = {FX_EXP_TAB_VALUES};
+static inline int fx_host_lo(double v) { uint64_t u; memcpy(&u, &v, 8); return (int)(uint32_t)u; }
+static inline int fx_host_hi(double v) { uint64_t u; memcpy(&u, &v, 8); return (int)(uint32_t)(u >> 32); }
+static inline double fx_host_hilo(int hi, int lo) {
+    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double v; memcpy(&v, &u, 8); return v;
+}
+#endif
+__host__ __device__ __forceinline__ double fx_exp_nonpos(double x) {
     x = fmax(x, -708.0);                               // below: 2^-1022 scale would go subnormal
     const double t = fma(x, 92.33248261689366, 6755399441055744.0);   // round-to-nearest via magic
+#ifdef __CUDA_ARCH__
     const int n = __double2loint(t);
+#else
+    const int n = fx_host_lo(t);
+#endif
     const double fn = t - 6755399441055744.0;
     double r = fma(fn, -0.010830424696905538, x);
     r = fma(fn, 6.563929801064195e-13, r);
@@ -214,10 +231,18 @@ __device__ __forceinline__ double fx_exp_nonpos(double x) {
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     const double p1 = p * r;                           // e^r - 1
+#ifdef __CUDA_ARCH__
     const double2 th = __ldg(reinterpret_cast<const double2*>(fx_exp_tab) + (n & 63));
-    const double v = th.x + fma(th.x, p1, th.y);       // in [1, 2): normal
+#else
+    const double2 th = make_double2(fx_exp_tab_host[2 * (n & 63)], fx_exp_tab_host[2 * (n & 63) + 1]);
+#endif
+    const double v = th.x + fma(th.x, p1, th.y);       // in (0.99, 2): normal
     // scale by 2^(n >> 6) in the exponent field (n >> 6 >= -1022: the result stays normal)
+#ifdef __CUDA_ARCH__
     return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+#else
+    return fx_host_hilo(fx_host_hi(v) + ((n >> 6) << 20), fx_host_lo(v));
+#endif
 }
 
 // kernel map of a dot product (and squared norms for the Gaussian), see include/fxb200.h
