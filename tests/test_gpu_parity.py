@@ -486,3 +486,14 @@ def test_float32_inputs_keep_their_eltype(gpu_ctx):
     np.testing.assert_allclose(np.abs(D)[:5], np.abs(D2), rtol=1e-5)
     T = fxb200.transform_kpca(X, fxb200.GaussianKernel(0.5), V[:, :2].astype(np.float32), X, ctx=gpu_ctx)
     assert T.dtype == np.float32 and T.shape == (20, 2)
+
+
+# ------------------------------------------------------------------ a plain C host
+def test_plain_c_caller(tmp_path):
+    """tests/host/abi_smoke.c (C99, no Python in the loop) fits, transforms and checks the in-sample
+    identity through the C ABI."""
+    import subprocess
+    from test_library_abi import build_c_smoke
+    exe = build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "C_ABI_OK" in r.stdout, r.stdout + r.stderr

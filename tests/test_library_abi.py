@@ -170,3 +170,23 @@ def test_ctypes_prototypes_match_header():
             assert hret == "cstr", name
         else:
             assert kind.get(restype, "ptr") == hret, name
+
+
+def build_c_smoke(tmp_path):
+    """gcc -std=c99 -pedantic build of tests/host/abi_smoke.c against the in-tree library."""
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(fxb200.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-o", exe,
+                        os.path.join(ROOT, "tests", "host", "abi_smoke.c"), "-L" + libdir, "-lfxb200", "-lm",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_valid_c99_and_c_caller_fails_loudly_without_gpu(tmp_path):
+    import torch
+    exe = build_c_smoke(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present (the GPU leg is tests/test_gpu_parity.py::test_plain_c_caller)")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
