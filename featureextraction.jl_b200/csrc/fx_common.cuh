@@ -215,7 +215,18 @@ static inline double fx_host_hilo(int hi, int lo) {
 }
 #endif
 __host__ __device__ __forceinline__ double fx_exp_nonpos(double x) {
-    x = fmax(x, -708.0);                               // below: 2^-1022 scale would go subnormal
+    // clamp at -708 (below, the 2^m scale would leave the normal range).  For x <= 0 the high word,
+    // read as unsigned, grows with |x|, so one integer min on it does the job (-708.0 is
+    // 0xC0862000'00000000; the low word is kept, i.e. the clamp lands in [-708.0007, -708]);
+    // small positive x (high word < 0x80000000) pass unchanged.  fmax() costs five instructions.
+#ifdef __CUDA_ARCH__
+    x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC0862000u), __double2loint(x));
+#else
+    {
+        const unsigned h = (unsigned)fx_host_hi(x);
+        x = fx_host_hilo((int)(h < 0xC0862000u ? h : 0xC0862000u), fx_host_lo(x));
+    }
+#endif
     const double t = fma(x, 92.33248261689366, 6755399441055744.0);   // round-to-nearest via magic
 #ifdef __CUDA_ARCH__
     const int n = __double2loint(t);
@@ -278,6 +289,15 @@ __device__ __forceinline__ double kernel_map_t(const KernelMap& km, double dot, 
         const double base = fma(km.p0, dot, km.p1);
         return KID == 4 ? base : (KID == 5 ? base * base : (base * base) * base);
     }
+}
+// Gaussian map with the norms already multiplied by -gamma (gram.cu scales them once per tile):
+// exp(-gamma (ni + nj - 2 dot)) = exp(fma(2 gamma, dot, ni' + nj')), two FP64 operations before
+// the exp instead of three.
+__device__ __forceinline__ double gaussian_map_prescaled(double two_gamma, double dot, double nis, double njs,
+                                                         bool same_point) {
+    double x = fma(two_gamma, dot, nis + njs);
+    x = same_point ? 0.0 : x;
+    return fx_exp_nonpos(x);
 }
 static __host__ __device__ __forceinline__ int kernel_variant(int id, int ipow) {
     if (id == FX_KERNEL_GAUSSIAN) return 0;

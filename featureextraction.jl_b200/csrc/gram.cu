@@ -106,6 +106,13 @@ __device__ __forceinline__ void tile_coords(const GramParams& p, long tile, long
 
 __device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// Map of one element; for the Gaussian kernel (KID 0) the norms arrive pre-scaled by -gamma.
+template <int KID>
+__device__ __forceinline__ double gram_map(const KernelMap& km, double dot, double ni, double nj, bool same) {
+    if (KID == 0) return gaussian_map_prescaled(2.0 * km.p0, dot, ni, nj, same);
+    return kernel_map_t<KID>(km, dot, ni, nj, same);
+}
+
 // Kernel map + row sums + stores for one warp's 64x32 accumulator tile.  EDGE tiles (ragged
 // borders or touching the diagonal) carry the validity masks and the same-point test; interior
 // tiles run the bare arithmetic.
@@ -126,13 +133,13 @@ __device__ __forceinline__ void gram_epilogue_plain(const GramParams& p, double 
             double v0, v1;
             if (EDGE) {
                 const long j = jb + nt * 8;
-                v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], ig == j);
-                v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], ig == j + 1);
+                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], ig == j);
+                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], ig == j + 1);
                 v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
                 v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
             } else {
-                v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], false);
-                v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], false);
+                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], false);
+                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], false);
             }
             *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(v0, v1);
             sacc += v0 + v1;
@@ -169,7 +176,7 @@ __device__ __forceinline__ void gram_epilogue_mirror(const GramParams& p, double
         double nb0 = 0.0, nb1 = 0.0;
         if (KID == 0) {
             const double2 v = __ldg(reinterpret_cast<const double2*>(p.nb + jb + nt * 8));
-            nb0 = v.x; nb1 = v.y;
+            nb0 = -p.km.p0 * v.x; nb1 = -p.km.p0 * v.y;
         }
         if (nt >= 2) {
             // the bulk stores issued from this buffer two groups ago must have read it
@@ -184,13 +191,13 @@ __device__ __forceinline__ void gram_epilogue_mirror(const GramParams& p, double
                 const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
                 const bool iv = i < p.rows_valid;
                 const long j = jb + nt * 8;
-                v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, ig == j);
-                v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, ig == j + 1);
+                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, ig == j);
+                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, ig == j + 1);
                 v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
                 v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
             } else {
-                v0 = kernel_map_t<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, false);
-                v1 = kernel_map_t<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, false);
+                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, false);
+                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, false);
             }
             *reinterpret_cast<double2*>(p.K + i * p.ldk + jb + nt * 8) = make_double2(v0, v1);
             tb[(2 * t) * TS + mt * 8 + g] = v0;              // transposed: row = column of the tile
@@ -308,13 +315,13 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         // squared norms for the Gaussian map: requested now, consumed after the main loop
         double ni[8], nbv[4][2];
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) ni[mt] = (KID == 0) ? p.na[i0 + wm * 64 + mt * 8 + g] : 0.0;
+        for (int mt = 0; mt < 8; ++mt) ni[mt] = (KID == 0) ? -p.km.p0 * p.na[i0 + wm * 64 + mt * 8 + g] : 0.0;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             nbv[nt][0] = nbv[nt][1] = 0.0;
             if (KID == 0) {
                 const double2 v = *reinterpret_cast<const double2*>(p.nb + j0 + wn * 32 + nt * 8 + 2 * t);
-                nbv[nt][0] = v.x; nbv[nt][1] = v.y;
+                nbv[nt][0] = -p.km.p0 * v.x; nbv[nt][1] = -p.km.p0 * v.y;   // pre-scaled by -gamma (gram_map)
             }
         }
 
