@@ -22,10 +22,11 @@
 // STRAIGHT INTO THE PEER'S K over NVLink (plain st.global to the IPC-mapped address), so every
 // rank executes ~half of its row block and no separate exchange step exists.
 #include "fx_kernels.cuh"
+#include "gram_tiles.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3;
+constexpr int BM = FX_GRAM_BM, BN = FX_GRAM_BN, BK = 16, STAGES = 3;
 constexpr int AS = BM + 4;                      // 132: (t*AS + g) mod 16 distinct for t,g in 0..3
 constexpr int BS = BN + 4;                      // 68
 constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25600 B)
@@ -58,51 +59,7 @@ struct GramParams {
     KernelMap km;
 };
 
-// What this rank does with tile (ty, tx): 0 = skip (someone's mirror store produces it),
-// 1 = compute, 2 = compute and mirror into block `peer` (== own block inside the diagonal block).
-__device__ __forceinline__ int tile_role(const GramParams& p, int ty, int tx, int& peer) {
-    peer = p.rank;
-    if (!p.sym) return 1;
-    const int bw = 2 * p.tiles_y;                                 // tile-columns per rank block
-    const int c = (p.sym == 2) ? tx / bw : ((tx >= (int)(p.diag_shift / BN) && tx < (int)(p.diag_shift / BN) + bw) ? p.rank : -1);
-    if (c == p.rank) {
-        const int rel = tx - (int)(p.diag_shift / BN);
-        if (rel < 2 * ty) return 0;                               // left of the diagonal
-        return rel >= 2 * ty + 2 ? 2 : 1;
-    }
-    if (p.sym != 2) return 1;
-    const int delta = (c - p.rank + p.world) % p.world;
-    bool own;
-    if (2 * delta < p.world) own = true;
-    else if (2 * delta > p.world) own = false;
-    else own = (((ty + (tx - c * bw) / 2) & 1) == (p.rank < c ? 0 : 1));   // opposite blocks: checkerboard
-    peer = c;
-    return own ? 2 : 0;
-}
-
-// Tile order: column panels of PANEL tile-columns swept over all row blocks, so that the panel's
-// slab of the column operand (PANEL x 131 KB at d=256) stays L2-resident while the row operand
-// streams; a plain row-major sweep re-reads all of X from HBM once per row block.
-// sym == 2: the sweep goes rank block by rank block and starts at the rank's OWN block
-// (c = rank, rank+1, ... mod world), so that at any moment the ranks mirror into pairwise distinct
-// peers (a permutation over NVSwitch) instead of all into the same one.
-constexpr int PANEL = 128;
-__device__ __forceinline__ void tile_coords(const GramParams& p, long tile, long& i0, long& j0, int& tx) {
-    const int nblk = (p.sym == 2) ? p.world : 1;
-    const int bw = p.tiles_x / nblk;                           // tile-columns per block
-    const long per_block = (long)bw * p.tiles_y;
-    const int kb = (int)(tile / per_block);
-    const long inblk = tile - (long)kb * per_block;
-    const long per_panel = (long)PANEL * p.tiles_y;
-    const int panel = (int)(inblk / per_panel);
-    const long within = inblk - (long)panel * per_panel;
-    const int pw = min(PANEL, bw - panel * PANEL);             // last panel of a block may be narrower
-    const int ty = (int)(within / pw);
-    const int blk = (p.sym == 2) ? (p.rank + kb) % p.world : 0;
-    tx = blk * bw + panel * PANEL + (int)(within - (long)ty * pw);
-    i0 = (long)ty * BM;
-    j0 = (long)tx * BN;
-}
+// tile_role() / tile_coords(): gram_tiles.cuh (host-testable)
 
 __device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
