@@ -190,3 +190,47 @@ def test_header_is_valid_c99_and_c_caller_fails_loudly_without_gpu(tmp_path):
         pytest.skip("GPU present (the GPU leg is tests/test_gpu_parity.py::test_plain_c_caller)")
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+def test_sharding_properties_hypothesis():
+    """Random (n, world): the row partition covers [0, n) exactly with only trailing padding, the
+    query partition is a contiguous cover, and the symmetric-Gram ownership stays exact-once and
+    balanced (property test over the Python restatement; the C++ side is tied to it by
+    tests/test_device_math_host.py)."""
+    from hypothesis import given, settings, strategies as st
+    import numpy as np
+    from fxb200.sharding import row_partition, query_partition, gram_tile_roles
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 4000), world=st.integers(1, 8), m=st.integers(0, 10**7))
+    def prop(n, world, m):
+        ld, n_ld, parts = row_partition(n, world)
+        assert ld % 128 == 0 and n_ld == ld * world and n_ld >= n
+        assert sum(r for _, r in parts) == n
+        nxt = 0
+        for row0, rows in parts:
+            assert row0 % ld == 0 and 0 <= rows <= ld
+            if rows:
+                assert row0 == nxt        # valid rows are contiguous in the global index space
+                nxt += rows
+            if rows < ld:
+                nxt = n                   # only the last non-empty rank is ragged
+        qp = query_partition(m, world)
+        assert sum(c for _, c in qp) == m and all(qp[i][0] + qp[i][1] == qp[i + 1][0] for i in range(world - 1))
+        ty_n = ld // 128
+        cells = np.zeros((2 * ty_n * world, 2 * ty_n * world), dtype=np.int64)
+        ex = []
+        for r in range(world):
+            role, target = gram_tile_roles(n, world, r, peer=True)
+            ex.append(int((role > 0).sum()))
+            tys, txs = np.nonzero(role)
+            for ty, tx in zip(tys, txs):
+                gi = 2 * (r * ty_n + ty)
+                cells[gi:gi + 2, tx] += 1
+                if role[ty, tx] == 2:
+                    assert tx // (2 * ty_n) == target[ty, tx]
+                    cells[tx, gi:gi + 2] += 1
+        assert (cells == 1).all()
+        assert max(ex) - min(ex) <= max(2, ty_n)      # an odd checkerboard leaves one super-tile (2 tiles) over
+
+    prop()
