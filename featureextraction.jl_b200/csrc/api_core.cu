@@ -213,13 +213,13 @@ static int ctx_common_init(int device, fx_ctx** out) {
 extern "C" int fx_init(int device, fx_ctx** out) { return ctx_common_init(device, out); }
 
 extern "C" int fx_comm_unique_id(void* id128) {
-    if (!id128) return -1;
+    if (!id128) { fx_set_error("fx_comm_unique_id: invalid argument 1 (!id128)"); return -1; }
     return fxcomm_unique_id(id128);
 }
 
 extern "C" int fx_init_distributed(int device, int rank, int world, const void* id128, fx_ctx** out) {
     if (world < 1 || rank < 0 || rank >= world) { fx_set_error("bad rank/world %d/%d", rank, world); return -2; }
-    if (!id128 && world > 1) return -4;
+    if (!id128 && world > 1) { fx_set_error("fx_init_distributed: invalid argument 4 (!id128 && world > 1)"); return -4; }
     FX_TRY(ctx_common_init(device, out));
     fx_ctx* c = *out;
     c->rank = rank;
@@ -232,7 +232,7 @@ extern "C" int fx_init_distributed(int device, int rank, int world, const void* 
 }
 
 extern "C" int fx_set_stream(fx_ctx* ctx, void* cuda_stream) {
-    if (!ctx) return -1;
+    if (!ctx) { fx_set_error("fx_set_stream: ctx is NULL"); return -1; }
     cudaSetDevice(ctx->device);
     if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (cuda_stream) {
@@ -246,7 +246,7 @@ extern "C" int fx_set_stream(fx_ctx* ctx, void* cuda_stream) {
 }
 
 extern "C" int fx_ctx_info(const fx_ctx* ctx, int* device, int* rank, int* world, int* sm_count) {
-    if (!ctx) return -1;
+    if (!ctx) { fx_set_error("fx_ctx_info: ctx is NULL"); return -1; }
     if (device) *device = ctx->device;
     if (rank) *rank = ctx->rank;
     if (world) *world = ctx->world;
@@ -286,7 +286,7 @@ extern "C" void fx_model_free(fx_model* m) {
 }
 
 extern "C" int fx_model_info(const fx_model* m, int64_t* n, int64_t* d, int* k, int* kernel_id) {
-    if (!m) return -1;
+    if (!m) { fx_set_error("fx_model_info: model is NULL"); return -1; }
     if (n) *n = m->n;
     if (d) *d = m->d;
     if (k) *k = m->k;

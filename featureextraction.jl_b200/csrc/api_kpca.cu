@@ -350,22 +350,22 @@ extern "C" int fx_gram_f64(fx_ctx* ctx, const double* Z, int64_t m, int64_t ldz,
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
-    if (!ctx) return -1;
+    if (!ctx) { fx_set_error("fx_gram_f64: ctx is NULL"); return -1; }
     const bool sym = (Z == nullptr);
     if (sym) { m = n; }
-    if (m < 1) return -2;
-    if (!sym && ldz < m) return -3;
-    if (!X) return -4;
-    if (n < 1) return -5;
-    if (ldx < n) return -6;
-    if (d < 1) return -7;
+    if (m < 1) { fx_set_error("fx_gram_f64: invalid argument 2 (m < 1)"); return -2; }
+    if (!sym && ldz < m) { fx_set_error("fx_gram_f64: invalid argument 3 (!sym && ldz < m; DimensionMismatch)"); return -3; }
+    if (!X) { fx_set_error("fx_gram_f64: invalid argument 4 (!X)"); return -4; }
+    if (n < 1) { fx_set_error("fx_gram_f64: invalid argument 5 (n < 1)"); return -5; }
+    if (ldx < n) { fx_set_error("fx_gram_f64: invalid argument 6 (ldx < n; DimensionMismatch)"); return -6; }
+    if (d < 1) { fx_set_error("fx_gram_f64: invalid argument 7 (d < 1)"); return -7; }
     double kpv[3]; int ipow;
     if (!kparams || fx_make_kernel_map(kernel_id, kparams, &ipow, kpv)) {
         fx_set_error("gram: unknown kernel id or invalid parameters");
         return -8;
     }
-    if (!K) return -11;
-    if (ldk < m) return -12;
+    if (!K) { fx_set_error("fx_gram_f64: invalid argument 11 (!K)"); return -11; }
+    if (ldk < m) { fx_set_error("fx_gram_f64: invalid argument 12 (ldk < m; DimensionMismatch)"); return -12; }
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
     // device result is row-major [n_pad][m_ld] = column-major m x n with leading dimension m_ld
@@ -413,9 +413,9 @@ extern "C" int fx_center_f64(fx_ctx* ctx, double* K, int64_t n, int64_t ldk, dou
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
-    if (!ctx) return -1;
-    if (!K) return -2;
-    if (n < 1) return -3;
+    if (!ctx) { fx_set_error("fx_center_f64: ctx is NULL"); return -1; }
+    if (!K) { fx_set_error("fx_center_f64: invalid argument 2 (!K)"); return -2; }
+    if (n < 1) { fx_set_error("fx_center_f64: invalid argument 3 (n < 1)"); return -3; }
     if (ldk < n) { fx_set_error("center: ldk < n (DimensionMismatch)"); return -4; }
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
@@ -453,15 +453,15 @@ extern "C" int fx_symm_f64(fx_ctx* ctx, const double* K, int64_t n, int64_t ldk,
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
-    if (!ctx) return -1;
-    if (!K) return -2;
-    if (n < 1) return -3;
-    if (ldk < n) return -4;
-    if (!V) return -5;
+    if (!ctx) { fx_set_error("fx_symm_f64: ctx is NULL"); return -1; }
+    if (!K) { fx_set_error("fx_symm_f64: invalid argument 2 (!K)"); return -2; }
+    if (n < 1) { fx_set_error("fx_symm_f64: invalid argument 3 (n < 1)"); return -3; }
+    if (ldk < n) { fx_set_error("fx_symm_f64: invalid argument 4 (ldk < n; DimensionMismatch)"); return -4; }
+    if (!V) { fx_set_error("fx_symm_f64: invalid argument 5 (!V)"); return -5; }
     if (b < 1 || b > 64) { fx_set_error("symm: block width must be 1..64"); return -6; }
-    if (ldv < n) return -7;
-    if (!Y) return -8;
-    if (ldy < n) return -9;
+    if (ldv < n) { fx_set_error("fx_symm_f64: invalid argument 7 (ldv < n; DimensionMismatch)"); return -7; }
+    if (!Y) { fx_set_error("fx_symm_f64: invalid argument 8 (!Y)"); return -8; }
+    if (ldy < n) { fx_set_error("fx_symm_f64: invalid argument 9 (ldy < n; DimensionMismatch)"); return -9; }
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
     const int64_t np = round_up(n, 128);
@@ -498,11 +498,11 @@ extern "C" int fx_symm_f64(fx_ctx* ctx, const double* K, int64_t n, int64_t ldk,
 }
 
 extern "C" int fx_syevd_small_f64(fx_ctx* ctx, double* A, int m, int64_t lda, double* w, int* sweeps) {
-    if (!ctx) return -1;
-    if (!A) return -2;
+    if (!ctx) { fx_set_error("fx_syevd_small_f64: ctx is NULL"); return -1; }
+    if (!A) { fx_set_error("fx_syevd_small_f64: invalid argument 2 (!A)"); return -2; }
     if (m < 1 || m > 1024) { fx_set_error("syevd_small: order must be 1..1024"); return -3; }
     if (lda < m) { fx_set_error("syevd_small: lda < m (DimensionMismatch)"); return -4; }
-    if (!w) return -5;
+    if (!w) { fx_set_error("fx_syevd_small_f64: invalid argument 5 (!w)"); return -5; }
     FX_CUDA(cudaSetDevice(ctx->device));
     size_t need = 3 * fx_align256((size_t)m * m * 8) + fx_align256((size_t)m * 8) + 8192;
     FX_TRY(fx_arena_reserve(ctx, need));

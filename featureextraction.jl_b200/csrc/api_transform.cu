@@ -11,12 +11,12 @@ int transform_impl(fx_ctx* ctx, const fx_model* md, const double* Z, bool on_dev
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
-    if (!ctx) return -1;
+    if (!ctx) { fx_set_error("transform: ctx is NULL"); return -1; }
     if (!md) { fx_set_error("transform: model is NULL"); return -2; }
-    if (!Z) return -3;
-    if (m < 1) return -4;
+    if (!Z) { fx_set_error("transform_impl: invalid argument 3 (!Z)"); return -3; }
+    if (m < 1) { fx_set_error("transform_impl: invalid argument 4 (m < 1)"); return -4; }
     if (ldz < m) { fx_set_error("transform: ldz < m (DimensionMismatch)"); return -5; }
-    if (!out) return -6;
+    if (!out) { fx_set_error("transform_impl: invalid argument 6 (!out)"); return -6; }
     if (ldo < m) { fx_set_error("transform: ldo < m (DimensionMismatch)"); return -7; }
     if (md->device != ctx->device) { fx_set_error("transform: model lives on another device"); return -2; }
     FX_CUDA(cudaSetDevice(ctx->device));
@@ -106,20 +106,20 @@ extern "C" int fx_model_create_f64(fx_ctx* ctx, const double* X, int64_t n, int6
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
-    if (!ctx) return -1;
-    if (!X) return -2;
-    if (n < 1) return -3;
-    if (d < 1) return -4;
+    if (!ctx) { fx_set_error("fx_model_create_f64: ctx is NULL"); return -1; }
+    if (!X) { fx_set_error("fx_model_create_f64: invalid argument 2 (!X)"); return -2; }
+    if (n < 1) { fx_set_error("fx_model_create_f64: invalid argument 3 (n < 1)"); return -3; }
+    if (d < 1) { fx_set_error("fx_model_create_f64: invalid argument 4 (d < 1)"); return -4; }
     if (ldx < n) { fx_set_error("model_create: ldx < n (DimensionMismatch)"); return -5; }
     double kpv[3]; int ipow;
     if (!kparams || fx_make_kernel_map(kernel_id, kparams, &ipow, kpv)) {
         fx_set_error("model_create: unknown kernel id or invalid parameters");
         return -6;
     }
-    if (!W) return -8;
+    if (!W) { fx_set_error("fx_model_create_f64: invalid argument 8 (!W)"); return -8; }
     if (k < 1 || k > 64) { fx_set_error("model_create: k must be 1..64"); return -9; }
     if (ldw < n) { fx_set_error("model_create: ldw < n (DimensionMismatch: W must have n rows)"); return -10; }
-    if (!model) return -12;
+    if (!model) { fx_set_error("model is NULL"); return -12; }
     *model = nullptr;
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;

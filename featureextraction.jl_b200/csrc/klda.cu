@@ -164,20 +164,20 @@ extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t 
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (model) *model = nullptr;
-    if (!ctx) return -1;
-    if (!X) return -2;
-    if (n < 2) return -3;
-    if (d < 1) return -4;
+    if (!ctx) { fx_set_error("fx_klda_fit_f64: ctx is NULL"); return -1; }
+    if (!X) { fx_set_error("fx_klda_fit_f64: invalid argument 2 (!X)"); return -2; }
+    if (n < 2) { fx_set_error("fx_klda_fit_f64: invalid argument 3 (n < 2)"); return -3; }
+    if (d < 1) { fx_set_error("fx_klda_fit_f64: invalid argument 4 (d < 1)"); return -4; }
     if (ldx < n) { fx_set_error("klda_fit: ldx < n (DimensionMismatch)"); return -5; }
     double kpv[3]; int ipow;
     if (!kparams || fx_make_kernel_map(kernel_id, kparams, &ipow, kpv)) {
         fx_set_error("klda_fit: unknown kernel id or invalid kernel parameters");
         return -6;
     }
-    if (!y) return -8;
+    if (!y) { fx_set_error("fx_klda_fit_f64: invalid argument 8 (!y)"); return -8; }
     const int c = nclass;
     if (c < 2 || c > 64 || c >= n) { fx_set_error("klda_fit: nclass must lie in 2..64 and be < n"); return -9; }
-    if (!freq) return -10;
+    if (!freq) { fx_set_error("fx_klda_fit_f64: invalid argument 10 (!freq)"); return -10; }
     if (alpha_b != 0.0 || eps_b != 0.0) {
         fx_set_error("klda_fit: alpha_b / eps_b != 0 is not supported (Sigma_b must stay rank <= c for the "
                      "reduced c x c eigenproblem)");
@@ -190,9 +190,9 @@ extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t 
         return FX_ERR_NOT_POSDEF;
     }
     if (ncomp < 1 || ncomp > c) { fx_set_error("klda_fit: ncomp must lie in 1..nclass"); return -15; }
-    if (!A) return -17;
+    if (!A) { fx_set_error("fx_klda_fit_f64: invalid argument 17 (!A)"); return -17; }
     if (lda < n) { fx_set_error("klda_fit: lda < n (DimensionMismatch)"); return -18; }
-    if (!lambda) return -19;
+    if (!lambda) { fx_set_error("fx_klda_fit_f64: invalid argument 19 (!lambda)"); return -19; }
     std::vector<double> inv_cnt(c, 0.0), hfreq(freq, freq + c);
     {
         std::vector<int64_t> cnt(c, 0);

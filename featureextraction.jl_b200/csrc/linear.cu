@@ -122,16 +122,16 @@ extern "C" int fx_pca_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, in
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
-    if (!ctx) return -1;
-    if (!X) return -2;
-    if (n < 2) return -3;
+    if (!ctx) { fx_set_error("fx_pca_f64: ctx is NULL"); return -1; }
+    if (!X) { fx_set_error("fx_pca_f64: invalid argument 2 (!X)"); return -2; }
+    if (n < 2) { fx_set_error("fx_pca_f64: invalid argument 3 (n < 2)"); return -3; }
     if (p < 1 || p > 512) { fx_set_error("pca: p must lie in 1..512"); return -4; }
     if (ldx < n) { fx_set_error("pca: ldx < n (DimensionMismatch)"); return -5; }
-    if (!(alpha >= 0.0 && alpha <= 1.0)) return -6;
-    if (!(eps >= 0.0)) return -7;
-    if (!V) return -8;
+    if (!(alpha >= 0.0 && alpha <= 1.0)) { fx_set_error("fx_pca_f64: invalid argument 6 (!(alpha >= 0.0 && alpha <= 1.0))"); return -6; }
+    if (!(eps >= 0.0)) { fx_set_error("fx_pca_f64: invalid argument 7 (!(eps >= 0.0))"); return -7; }
+    if (!V) { fx_set_error("fx_pca_f64: invalid argument 8 (!V)"); return -8; }
     if (ldv < p) { fx_set_error("pca: ldv < p (DimensionMismatch)"); return -9; }
-    if (!lambda) return -10;
+    if (!lambda) { fx_set_error("fx_pca_f64: invalid argument 10 (!lambda)"); return -10; }
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
     FX_TRY(fx_arena_reserve(ctx, lin_bytes(ctx, n, p)));
@@ -183,15 +183,15 @@ extern "C" int fx_project_f64(fx_ctx* ctx, const double* W, int64_t p, int k, in
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
-    if (!ctx) return -1;
-    if (!W) return -2;
+    if (!ctx) { fx_set_error("fx_project_f64: ctx is NULL"); return -1; }
+    if (!W) { fx_set_error("fx_project_f64: invalid argument 2 (!W)"); return -2; }
     if (p < 1 || p > 512) { fx_set_error("project: p must lie in 1..512"); return -3; }
-    if (k < 1 || k > 512) return -4;
+    if (k < 1 || k > 512) { fx_set_error("fx_project_f64: invalid argument 4 (k < 1 || k > 512)"); return -4; }
     if (ldw < p) { fx_set_error("project: ldw < p (DimensionMismatch)"); return -5; }
-    if (!Z) return -6;
-    if (m < 1) return -7;
+    if (!Z) { fx_set_error("fx_project_f64: invalid argument 6 (!Z)"); return -6; }
+    if (m < 1) { fx_set_error("fx_project_f64: invalid argument 7 (m < 1)"); return -7; }
     if (ldz < m) { fx_set_error("project: ldz < m (DimensionMismatch)"); return -8; }
-    if (!out) return -9;
+    if (!out) { fx_set_error("fx_project_f64: invalid argument 9 (!out)"); return -9; }
     if (ldo < m) { fx_set_error("project: ldo < m (DimensionMismatch)"); return -10; }
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
@@ -221,22 +221,22 @@ extern "C" int fx_lda_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, in
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
-    if (!ctx) return -1;
-    if (!X) return -2;
-    if (n < 2) return -3;
+    if (!ctx) { fx_set_error("fx_lda_f64: ctx is NULL"); return -1; }
+    if (!X) { fx_set_error("fx_lda_f64: invalid argument 2 (!X)"); return -2; }
+    if (n < 2) { fx_set_error("fx_lda_f64: invalid argument 3 (n < 2)"); return -3; }
     if (p < 1 || p > 512) { fx_set_error("lda: p must lie in 1..512"); return -4; }
     if (ldx < n) { fx_set_error("lda: ldx < n (DimensionMismatch)"); return -5; }
-    if (!y) return -6;
+    if (!y) { fx_set_error("fx_lda_f64: invalid argument 6 (!y)"); return -6; }
     const int k = nclass;
     if (k < 2 || k > 64 || k >= n) { fx_set_error("lda: nclass must lie in 2..64 and be < n"); return -7; }
-    if (!freq) return -8;
-    if (!(alpha_b >= 0.0 && alpha_b <= 1.0)) return -9;
-    if (!(eps_b >= 0.0)) return -10;
-    if (!(alpha_w >= 0.0 && alpha_w <= 1.0)) return -11;
-    if (!(eps_w >= 0.0)) return -12;
-    if (!V) return -13;
+    if (!freq) { fx_set_error("fx_lda_f64: invalid argument 8 (!freq)"); return -8; }
+    if (!(alpha_b >= 0.0 && alpha_b <= 1.0)) { fx_set_error("fx_lda_f64: invalid argument 9 (!(alpha_b >= 0.0 && alpha_b <= 1.0))"); return -9; }
+    if (!(eps_b >= 0.0)) { fx_set_error("fx_lda_f64: invalid argument 10 (!(eps_b >= 0.0))"); return -10; }
+    if (!(alpha_w >= 0.0 && alpha_w <= 1.0)) { fx_set_error("fx_lda_f64: invalid argument 11 (!(alpha_w >= 0.0 && alpha_w <= 1.0))"); return -11; }
+    if (!(eps_w >= 0.0)) { fx_set_error("fx_lda_f64: invalid argument 12 (!(eps_w >= 0.0))"); return -12; }
+    if (!V) { fx_set_error("fx_lda_f64: invalid argument 13 (!V)"); return -13; }
     if (ldv < p) { fx_set_error("lda: ldv < p (DimensionMismatch)"); return -14; }
-    if (!lambda) return -15;
+    if (!lambda) { fx_set_error("fx_lda_f64: invalid argument 15 (!lambda)"); return -15; }
     std::vector<double> inv_cnt(k, 0.0);
     {
         std::vector<int64_t> cnt(k, 0);

@@ -259,7 +259,7 @@ int fx_launch_transform_ex(fx_ctx* ctx, const TransformArgs& a, int variant, dou
     p.kt = (int)(a.d_pad / TBK); p.ntiles = (int)(a.n_ld / TN); p.nsplit = 1; p.kc = a.kcols;
     p.km.id = a.kernel_id; p.km.p0 = a.kp[0]; p.km.p1 = a.kp[1]; p.km.p2 = a.kp[2];
     double tmp[3];
-    if (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp)) return -1;
+    if (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp)) { fx_set_error("fx_launch_transform_ex: invalid argument 1 (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp))"); return -1; }
     if (variant != 0) {
         dim3 grid((unsigned)ceil_div(a.m_pad, 128), (unsigned)a.kcols);
         transform_naive_kernel<<<grid, 128, 0, ctx->stream>>>(p, (int)a.d_pad, a.m_pad);

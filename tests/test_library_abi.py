@@ -234,3 +234,27 @@ def test_sharding_properties_hypothesis():
         assert max(ex) - min(ex) <= max(2, ty_n)      # an odd checkerboard leaves one super-tile (2 tiles) over
 
     prop()
+
+
+def test_null_context_is_an_argument_error_everywhere():
+    """Every entry point that takes a context rejects NULL with a negative code (argument error,
+    the analogue of common.jl:87-89) instead of crashing -- callable without a GPU."""
+    lib = fxb200.load_library()
+    for name, (restype, argtypes) in fxb200.PROTOTYPES.items():
+        if restype is not ctypes.c_int or not argtypes or name in ("fx_init", "fx_init_distributed",
+                                                                    "fx_comm_unique_id", "fx_version"):
+            continue
+        args = []
+        for a in argtypes:
+            if a in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64):
+                args.append(a(8))
+            elif a is ctypes.c_double:
+                args.append(a(0.0))
+            else:
+                args.append(None)                   # every pointer NULL, the context first of all
+        rc = getattr(lib, name)(*args)
+        if name == "fx_ctx_peer_access":
+            assert rc == 0
+        else:
+            assert rc < 0, "%s(NULL, ...) returned %d" % (name, rc)
+            assert lib.fx_last_error()
