@@ -9,7 +9,8 @@
 module FeatureExtractionB200
 
 export GaussianKernel, PolynomialKernel, SigmoidKernel, kpca, transform_kpca, klda, transform_klda,
-       pca, transform_pca, lda, transform_lda, KPCAModel, fit_kpca
+       pca, transform_pca, lda, transform_lda, KPCAModel, fit_kpca, comm_unique_id,
+       distributed_context, use_context!, peer_access
 
 const libfx = get(ENV, "FXB200_LIB", "libfxb200.so")
 
@@ -25,12 +26,34 @@ kernel_id(::SigmoidKernel) = Cint(2); kparams(k::SigmoidKernel) = Float64[k.a, k
 
 mutable struct Context
     h::Ptr{Cvoid}
+    Context(h::Ptr{Cvoid}) = new(h)                     # adopt an existing handle (distributed_context)
     function Context(device::Integer = 0)
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:fx_init, libfx), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r), "fx_init")
         c = new(r[]); finalizer(x -> ccall((:fx_shutdown, libfx), Cvoid, (Ptr{Cvoid},), x.h), c); c
     end
 end
+
+# Multi-GPU: one Julia process per GPU (Distributed / MPI.jl).  Rank 0 draws the communicator id,
+# the host program ships the 128 bytes to every rank, every rank opens its context and installs it
+# with `use_context!`; the same `kpca(X, κ; k=...)` call on every rank then returns the full (V, Λ).
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:fx_comm_unique_id, libfx), Cint, (Ptr{Cvoid},), id), "fx_comm_unique_id")
+    id
+end
+function distributed_context(device::Integer, rank::Integer, world::Integer, id::Vector{UInt8})
+    length(id) == 128 || throw(ArgumentError("the communicator id has 128 bytes"))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:fx_init_distributed, libfx), Cint, (Cint, Cint, Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                device, rank, world, id, r), "fx_init_distributed")
+    c = Context(r[])
+    finalizer(x -> ccall((:fx_shutdown, libfx), Cvoid, (Ptr{Cvoid},), x.h), c)
+    c
+end
+use_context!(c::Context) = (default_ctx[] = c)
+# true if the last collective fit shared the symmetric blocks of K between GPUs over NVLink
+peer_access(c::Context) = ccall((:fx_ctx_peer_access, libfx), Cint, (Ptr{Cvoid},), c.h) != 0
 const default_ctx = Ref{Union{Nothing,Context}}(nothing)
 ctx() = (default_ctx[] === nothing && (default_ctx[] = Context(0)); default_ctx[])
 
