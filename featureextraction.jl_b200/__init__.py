@@ -11,7 +11,7 @@ from ._lib import (FxError, FxLibraryMissing, DimensionMismatch, SolverOpts, Sta
                    PROTOTYPES, load as load_library)
 from .kernels import Kernel, GaussianKernel, PolynomialKernel, SigmoidKernel, from_spec
 from .api import (Context, Model, default_context, make_opts, kpca, transform_kpca, klda,
-                  transform_klda, model_from_components, pca, transform_pca, lda, transform_lda, kernelmatrix, centerkernelmatrix, symm,
+                  transform_klda, model_from_components, pca, transform_pca, lda, transform_lda, kernelmatrix, centerkernelmatrix, symm, center_symm,
                   syevd_small, bench_kernel)
 from . import synth, sharding
 

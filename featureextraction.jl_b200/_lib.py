@@ -76,6 +76,8 @@ PROTOTYPES = {
     "fx_center_f64": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.POINTER(Stats)]),
     "fx_symm_f64": (C.c_int, [_P, _P, _I64, _I64, _P, C.c_int, _I64, _P, _I64, C.c_int,
                               C.POINTER(Stats)]),
+    "fx_center_symm_f64": (C.c_int, [_P, _P, _I64, _I64, _P, C.c_int, _I64, _P, _I64, _P, _P,
+                                     C.POINTER(Stats)]),
     "fx_syevd_small_f64": (C.c_int, [_P, _P, C.c_int, _I64, _P, C.POINTER(C.c_int)]),
     "fx_bench_kernel": (C.c_int, [_P, C.c_int, _I64, _I64, C.c_int, _I64, C.c_int, C.c_int, _P]),
 }

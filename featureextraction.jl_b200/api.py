@@ -354,6 +354,26 @@ def symm(K, V, *, ctx=None, variant=0):
     return Y
 
 
+def center_symm(K, V, *, ctx=None):
+    """The centring pass as a fit runs it: returns (K~, K~ V, colmean, grandmean) from the fused
+    centre-while-multiplying kernel (fx_center_symm_f64)."""
+    ctx = ctx or default_context()
+    K = np.array(K, dtype=np.float64, order="F", copy=True)
+    V = _f64_colmajor(V, "V")
+    if K.ndim != 2 or K.shape[0] != K.shape[1]:
+        raise _lib.DimensionMismatch("Matrix K must be square.")
+    n, b = V.shape
+    if K.shape[0] != n:
+        raise _lib.DimensionMismatch("K and V must have the same number of rows")
+    Y = np.empty((n, b), dtype=np.float64, order="F")
+    cm = np.empty(n)
+    gm = np.empty(1)
+    st = Stats()
+    check(ctx._lib.fx_center_symm_f64(ctx._h, _ptr(K), n, n, _ptr(V), b, n, _ptr(Y), n, _ptr(cm), _ptr(gm),
+                                      C.byref(st)), "center_symm")
+    return K, Y, cm, float(gm[0])
+
+
 def syevd_small(A, *, ctx=None):
     """Device Jacobi: returns (w descending, V, sweeps)."""
     ctx = ctx or default_context()

@@ -281,6 +281,7 @@ extern "C" void fx_model_free(fx_model* m) {
     cudaFree(m->norms);
     cudaFree(m->W);
     cudaFree(m->bias);
+    cudaFree(m->wsum);
     cudaFree(m->colmean);
     delete m;
 }

@@ -189,15 +189,35 @@ int fx_model_build(fx_ctx* ctx, const GramStage& g, int kernel_id, const double*
     FX_TRY(dmalloc(&m->Xp, (size_t)g.d_pad * g.n_ld));
     FX_TRY(dmalloc(&m->norms, g.n_ld));
     FX_TRY(dmalloc(&m->W, (size_t)m->k_pad * g.n_ld));
-    FX_TRY(dmalloc(&m->bias, 64));
+    FX_TRY(dmalloc(&m->bias, m->k_pad));
+    FX_TRY(dmalloc(&m->wsum, 2 * (size_t)m->k_pad));
     FX_TRY(dmalloc(&m->colmean, g.n_ld));
     FX_CUDA(cudaMemcpyAsync(m->Xp, g.Xp, (size_t)g.d_pad * g.n_ld * 8, cudaMemcpyDeviceToDevice, s));
     FX_CUDA(cudaMemcpyAsync(m->norms, g.norms, (size_t)g.n_ld * 8, cudaMemcpyDeviceToDevice, s));
     FX_CUDA(cudaMemcpyAsync(m->W, W, (size_t)m->k_pad * g.n_ld * 8, cudaMemcpyDeviceToDevice, s));
     FX_CUDA(cudaMemcpyAsync(m->colmean, g.colmean, (size_t)g.n_ld * 8, cudaMemcpyDeviceToDevice, s));
-    FX_CUDA(cudaMemsetAsync(m->bias, 0, 64 * 8, s));
-    if (centered) FX_TRY(fx_launch_bias(ctx, m->colmean, m->W, g.n_ld, g.n, m->k_pad, m->bias));
+    FX_CUDA(cudaMemsetAsync(m->bias, 0, (size_t)m->k_pad * 8, s));
+    if (centered) {
+        FX_TRY(fx_launch_bias(ctx, m->colmean, m->W, g.n_ld, g.n, m->k_pad, m->bias));
+        FX_CUDA(cudaMemcpyAsync(ctx->pinned + 160, g.scal, sizeof(double), cudaMemcpyDeviceToHost, s));
+        FX_TRY(fx_model_finish_centering(ctx, m));
+        m->grandmean = ctx->pinned[160];
+    }
     *out = mg.release();
+    return 0;
+}
+
+// wsum = 1'W and the decision whether the transform needs the per-query row-mean term: a column
+// counts as orthogonal to 1 when |1'w| is at rounding level of the sum (64 eps |w|_1).
+int fx_model_finish_centering(fx_ctx* ctx, fx_model* m) {
+    cudaStream_t s = ctx->stream;
+    FX_TRY(fx_launch_colsums(ctx, m->W, m->n_ld, m->n, m->k_pad, m->wsum));
+    std::vector<double> h(2 * (size_t)m->k_pad);
+    FX_CUDA(cudaMemcpyAsync(h.data(), m->wsum, h.size() * 8, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    m->need_rowmean = 0;
+    for (int c = 0; c < m->k; ++c)
+        if (fabs(h[c]) > 64.0 * 2.220446049250313e-16 * h[m->k_pad + c]) m->need_rowmean = 1;
     return 0;
 }
 
@@ -491,6 +511,69 @@ extern "C" int fx_symm_f64(fx_ctx* ctx, const double* K, int64_t n, int64_t ldk,
     tm.end();
     st->symm_launches = 1;
     FX_CUDA(cudaMemcpy2DAsync(Y, ldy * 8, Yd, np * 8, n * 8, b, cudaMemcpyDeviceToHost, s));
+    FX_TRY(tot.stop(ctx, &st->total_ms));
+    tm.resolve();
+    st->kernel_launches = ctx->launches - launches0;
+    return 0;
+}
+
+// The fused centring pass of a fit, exposed for elementwise parity tests: K is centred IN PLACE by
+// the same kernel instance that computes Y = K~ V (symm.cu, CENTER variant: centred in registers,
+// written back through the TMA store warp).  fx_center_f64 exercises the standalone kernel.
+extern "C" int fx_center_symm_f64(fx_ctx* ctx, double* K, int64_t n, int64_t ldk, const double* V, int b,
+                                  int64_t ldv, double* Y, int64_t ldy, double* colmean, double* grandmean,
+                                  fx_stats* stats) {
+    fx_stats local;
+    fx_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!ctx) { fx_set_error("fx_center_symm_f64: ctx is NULL"); return -1; }
+    if (!K) { fx_set_error("fx_center_symm_f64: invalid argument 2 (!K)"); return -2; }
+    if (n < 1) { fx_set_error("fx_center_symm_f64: invalid argument 3 (n < 1)"); return -3; }
+    if (ldk < n) { fx_set_error("fx_center_symm_f64: invalid argument 4 (ldk < n; DimensionMismatch)"); return -4; }
+    if (!V) { fx_set_error("fx_center_symm_f64: invalid argument 5 (!V)"); return -5; }
+    if (b < 1 || b > 64) { fx_set_error("fx_center_symm_f64: block width must be 1..64"); return -6; }
+    if (ldv < n) { fx_set_error("fx_center_symm_f64: invalid argument 7 (ldv < n; DimensionMismatch)"); return -7; }
+    if (!Y) { fx_set_error("fx_center_symm_f64: invalid argument 8 (!Y)"); return -8; }
+    if (ldy < n) { fx_set_error("fx_center_symm_f64: invalid argument 9 (ldy < n; DimensionMismatch)"); return -9; }
+    FX_CUDA(cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    const int64_t np = round_up(n, 128);
+    const int bp = (int)round_up(b, 8);
+    const int splits = fx_symm_splits(ctx, np, np);
+    size_t need = fx_align256((size_t)np * np * 8) + 2 * fx_align256((size_t)bp * np * 8) +
+                  fx_align256((size_t)splits * bp * np * 8) + 3 * fx_align256((size_t)np * 8) + 8192;
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+    cudaStream_t s = ctx->stream;
+    double* Kd = (double*)fx_arena_alloc(ctx, (size_t)np * np * 8);
+    double* Vd = (double*)fx_arena_alloc(ctx, (size_t)bp * np * 8);
+    double* Yd = (double*)fx_arena_alloc(ctx, (size_t)bp * np * 8);
+    double* Yp = (double*)fx_arena_alloc(ctx, (size_t)splits * bp * np * 8);
+    double* rs = (double*)fx_arena_alloc(ctx, (size_t)np * 8);
+    double* cm = (double*)fx_arena_alloc(ctx, (size_t)np * 8);
+    double* sc = (double*)fx_arena_alloc(ctx, 256);
+    TotalTimer tot;
+    FX_TRY(tot.start(ctx));
+    FxTimer tm(ctx);
+    FX_CUDA(cudaMemsetAsync(Kd, 0, (size_t)np * np * 8, s));
+    FX_CUDA(cudaMemsetAsync(Vd, 0, (size_t)bp * np * 8, s));
+    FX_CUDA(cudaMemsetAsync(rs, 0, (size_t)np * 8, s));
+    FX_CUDA(cudaMemcpy2DAsync(Kd, np * 8, K, ldk * 8, n * 8, n, cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemcpy2DAsync(Vd, np * 8, V, ldv * 8, n * 8, b, cudaMemcpyHostToDevice, s));
+    tm.begin(&st->center_ms);
+    FX_TRY(fx_launch_rowsums(ctx, Kd, np, n, n, rs));
+    FX_TRY(fx_launch_means(ctx, rs, n, np, cm, sc));
+    SymmArgs sa;
+    sa.K = Kd; sa.ldk = np; sa.rows_pad = np; sa.V = Vd; sa.ldr = np; sa.v_rank_stride = (int64_t)bp * np;
+    sa.bcols = bp; sa.Y = Yd; sa.Ypart = Yp; sa.splits = splits;
+    sa.center_colmean = cm; sa.center_grand = sc; sa.rows_valid = n; sa.cols_valid = n; sa.row0 = 0;
+    FX_TRY(fx_launch_symm(ctx, sa, 0));
+    tm.end();
+    st->center_launches = 1;
+    FX_CUDA(cudaMemcpy2DAsync(K, ldk * 8, Kd, np * 8, n * 8, n, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpy2DAsync(Y, ldy * 8, Yd, np * 8, n * 8, b, cudaMemcpyDeviceToHost, s));
+    if (colmean) FX_CUDA(cudaMemcpyAsync(colmean, cm, n * 8, cudaMemcpyDeviceToHost, s));
+    if (grandmean) FX_CUDA(cudaMemcpyAsync(grandmean, sc, 8, cudaMemcpyDeviceToHost, s));
     FX_TRY(tot.stop(ctx, &st->total_ms));
     tm.resolve();
     st->kernel_launches = ctx->launches - launches0;

@@ -22,9 +22,10 @@ int transform_impl(fx_ctx* ctx, const fx_model* md, const double* Z, bool on_dev
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
     const int kc = md->k_pad;
+    const int kchunk = kc < 64 ? kc : 64;            // components per launch (the kernel holds <= 64 columns)
     const int64_t mc_max = m < QCHUNK ? round_up(m, 128) : QCHUNK;
     int nsplit = 1;
-    const size_t scr = fx_transform_scratch(ctx, mc_max, md->n_ld, kc, &nsplit);
+    const size_t scr = fx_transform_scratch(ctx, mc_max, md->n_ld, kchunk, &nsplit);
     size_t need = fx_align256((size_t)md->d_pad * mc_max * 8) + fx_align256((size_t)mc_max * 8) +
                   fx_align256((size_t)kc * mc_max * 8) + fx_align256(scr * 8) + 8192;
     FX_TRY(fx_arena_reserve(ctx, need));
@@ -34,6 +35,7 @@ int transform_impl(fx_ctx* ctx, const fx_model* md, const double* Z, bool on_dev
     double* nz = (double*)fx_arena_alloc(ctx, (size_t)mc_max * 8);
     double* od = (double*)fx_arena_alloc(ctx, (size_t)kc * mc_max * 8);
     double* scratch = scr ? (double*)fx_arena_alloc(ctx, scr * 8) : nullptr;
+    const bool rowmean = md->centered && md->need_rowmean;
 
     cudaEvent_t e0, e1;
     FX_CUDA(cudaEventCreate(&e0));
@@ -44,7 +46,7 @@ int transform_impl(fx_ctx* ctx, const fx_model* md, const double* Z, bool on_dev
         const int64_t mc = (m - q0) < QCHUNK ? (m - q0) : QCHUNK;
         const int64_t mp = round_up(mc, 128);
         int ns = 1;
-        fx_transform_scratch(ctx, mp, md->n_ld, kc, &ns);
+        fx_transform_scratch(ctx, mp, md->n_ld, kchunk, &ns);
         if (ns > nsplit) ns = nsplit;
         tm.begin(&st->h2d_ms);
         FX_CUDA(cudaMemsetAsync(Zp, 0, (size_t)md->d_pad * mp * 8, s));
@@ -53,16 +55,20 @@ int transform_impl(fx_ctx* ctx, const fx_model* md, const double* Z, bool on_dev
         tm.end();
         if (!on_dev) st->h2d_bytes += mc * md->d * 8;
         FX_TRY(fx_launch_rownorms(ctx, Zp, mp, mp, md->d_pad, nz));
-        TransformArgs ta;
-        ta.Zp = Zp; ta.ldz = mp; ta.nz = nz; ta.Xp = md->Xp; ta.ldx = md->n_ld; ta.nx = md->norms;
-        ta.d_pad = md->d_pad; ta.m_pad = mp; ta.n_ld = md->n_ld; ta.n_valid = md->n;
-        ta.W = md->W; ta.ldw = md->n_ld; ta.kcols = kc; ta.bias = md->centered ? md->bias : nullptr;
-        ta.out = od; ta.ldo = mp; ta.kernel_id = md->kernel_id;
-        ta.kp[0] = md->kp[0]; ta.kp[1] = md->kp[1]; ta.kp[2] = md->kp[2];
-        tm.begin(&st->transform_ms);
-        FX_TRY(fx_launch_transform_ex(ctx, ta, variant, scratch, ns));
-        tm.end();
-        st->transform_launches++;
+        for (int c0 = 0; c0 < kc; c0 += 64) {
+            TransformArgs ta;
+            ta.Zp = Zp; ta.ldz = mp; ta.nz = nz; ta.Xp = md->Xp; ta.ldx = md->n_ld; ta.nx = md->norms;
+            ta.d_pad = md->d_pad; ta.m_pad = mp; ta.n_ld = md->n_ld; ta.n_valid = md->n;
+            ta.W = md->W + (size_t)c0 * md->n_ld; ta.ldw = md->n_ld; ta.kcols = (kc - c0) < 64 ? (kc - c0) : 64;
+            ta.bias = md->centered ? md->bias + c0 : nullptr;
+            ta.out = od + (size_t)c0 * mp; ta.ldo = mp; ta.kernel_id = md->kernel_id;
+            ta.kp[0] = md->kp[0]; ta.kp[1] = md->kp[1]; ta.kp[2] = md->kp[2];
+            if (rowmean) { ta.wsum = md->wsum + c0; ta.grand = md->grandmean; }
+            tm.begin(&st->transform_ms);
+            FX_TRY(fx_launch_transform_ex(ctx, ta, variant, scratch, ns));
+            tm.end();
+            st->transform_launches++;
+        }
         tm.begin(&st->d2h_ms);
         FX_CUDA(cudaMemcpy2DAsync(out + q0, ldo * 8, od, mp * 8, mc * 8, md->k,
                                   on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -117,7 +123,7 @@ extern "C" int fx_model_create_f64(fx_ctx* ctx, const double* X, int64_t n, int6
         return -6;
     }
     if (!W) { fx_set_error("fx_model_create_f64: invalid argument 8 (!W)"); return -8; }
-    if (k < 1 || k > 64) { fx_set_error("model_create: k must be 1..64"); return -9; }
+    if (k < 1 || k > n) { fx_set_error("model_create: k must lie in 1..n"); return -9; }
     if (ldw < n) { fx_set_error("model_create: ldw < n (DimensionMismatch: W must have n rows)"); return -10; }
     if (!model) { fx_set_error("model is NULL"); return -12; }
     *model = nullptr;
@@ -134,7 +140,8 @@ extern "C" int fx_model_create_f64(fx_ctx* ctx, const double* X, int64_t n, int6
     if (cudaMalloc((void**)&m->Xp, (size_t)d_pad * n_ld * 8) != cudaSuccess ||
         cudaMalloc((void**)&m->norms, (size_t)n_ld * 8) != cudaSuccess ||
         cudaMalloc((void**)&m->W, (size_t)kc * n_ld * 8) != cudaSuccess ||
-        cudaMalloc((void**)&m->bias, 64 * 8) != cudaSuccess ||
+        cudaMalloc((void**)&m->bias, (size_t)kc * 8) != cudaSuccess ||
+        cudaMalloc((void**)&m->wsum, 2 * (size_t)kc * 8) != cudaSuccess ||
         cudaMalloc((void**)&m->colmean, (size_t)n_ld * 8) != cudaSuccess) {
         cudaGetLastError();
         fx_set_error("model_create: out of device memory");
@@ -146,29 +153,37 @@ extern "C" int fx_model_create_f64(fx_ctx* ctx, const double* X, int64_t n, int6
     MC(cudaMemcpy2DAsync(m->Xp, n_ld * 8, X, ldx * 8, n * 8, d, cudaMemcpyHostToDevice, s));
     MC(cudaMemsetAsync(m->W, 0, (size_t)kc * n_ld * 8, s));
     MC(cudaMemcpy2DAsync(m->W, n_ld * 8, W, ldw * 8, n * 8, k, cudaMemcpyHostToDevice, s));
-    MC(cudaMemsetAsync(m->bias, 0, 64 * 8, s));
+    MC(cudaMemsetAsync(m->bias, 0, (size_t)kc * 8, s));
+    MC(cudaMemsetAsync(m->wsum, 0, 2 * (size_t)kc * 8, s));
     MC(cudaMemsetAsync(m->colmean, 0, (size_t)n_ld * 8, s));
     if ((rc = fx_launch_rownorms(ctx, m->Xp, n_ld, n_ld, d_pad, m->norms))) return fail(rc);
     st->h2d_bytes = n * d * 8 + n * k * 8;
     if (center) {
-        // bias = r'W = (1/n) 1' K W = column means of the uncentred in-sample projection
+        // Column means r = K 1 / n and the grand mean of the training kernel matrix: the row sums of
+        // k(X, X) fall out of one in-sample pass of the fused kernel (its projection onto the first 8
+        // components is discarded); then bias = r'W, wsum = 1'W.
         int nsplit = 1;
-        const size_t scr = fx_transform_scratch(ctx, n_ld, n_ld, kc, &nsplit);
-        size_t need = 2 * fx_align256((size_t)kc * n_ld * 8) + fx_align256(scr * 8) + fx_align256((size_t)n_ld * 8) + 8192;
+        const size_t scr = fx_transform_scratch(ctx, n_ld, n_ld, 8, &nsplit);
+        size_t need = fx_align256((size_t)8 * n_ld * 8) + fx_align256(scr * 8) + 2 * fx_align256((size_t)n_ld * 8) + 8192;
         if ((rc = fx_arena_reserve(ctx, need))) return fail(rc);
         fx_arena_reset(ctx);
-        double* T = (double*)fx_arena_alloc(ctx, (size_t)kc * n_ld * 8);
-        double* ones = (double*)fx_arena_alloc(ctx, (size_t)n_ld * 8);
+        double* T = (double*)fx_arena_alloc(ctx, (size_t)8 * n_ld * 8);
+        double* rsum = (double*)fx_arena_alloc(ctx, (size_t)n_ld * 8);
+        double* gdev = (double*)fx_arena_alloc(ctx, 256);
         double* scratch = scr ? (double*)fx_arena_alloc(ctx, scr * 8) : nullptr;
         TransformArgs ta;
         ta.Zp = m->Xp; ta.ldz = n_ld; ta.nz = m->norms; ta.Xp = m->Xp; ta.ldx = n_ld; ta.nx = m->norms;
         ta.d_pad = d_pad; ta.m_pad = n_ld; ta.n_ld = n_ld; ta.n_valid = n; ta.W = m->W; ta.ldw = n_ld;
-        ta.kcols = kc; ta.bias = nullptr; ta.out = T; ta.ldo = n_ld; ta.kernel_id = kernel_id;
+        ta.kcols = 8; ta.bias = nullptr; ta.out = T; ta.ldo = n_ld; ta.kernel_id = kernel_id;
         ta.kp[0] = kpv[0]; ta.kp[1] = kpv[1]; ta.kp[2] = kpv[2];
+        ta.rz_out = rsum;
         if ((rc = fx_launch_transform_ex(ctx, ta, 0, scratch, nsplit))) return fail(rc);
         st->transform_launches = 1;
-        if ((rc = fx_launch_fill(ctx, ones, n_ld, 1.0 / (double)n))) return fail(rc);
-        if ((rc = fx_launch_bias(ctx, ones, T, n_ld, n, kc, m->bias))) return fail(rc);
+        if ((rc = fx_launch_means(ctx, rsum, n, n_ld, m->colmean, gdev))) return fail(rc);
+        if ((rc = fx_launch_bias(ctx, m->colmean, m->W, n_ld, n, kc, m->bias))) return fail(rc);
+        MC(cudaMemcpyAsync(ctx->pinned + 160, gdev, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if ((rc = fx_model_finish_centering(ctx, m))) return fail(rc);
+        m->grandmean = ctx->pinned[160];
     }
     MC(cudaStreamSynchronize(s));
 #undef MC

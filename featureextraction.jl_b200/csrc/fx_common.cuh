@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <unordered_set>
 #include <vector>
 #include "../../include/fxb200.h"
 
@@ -79,7 +80,13 @@ struct fx_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     int64_t launches = 0;
+    // kernels whose opt-in shared-memory attribute has been set on THIS device (the attribute is
+    // per device / context, so the registry lives here and not in a process-wide static)
+    std::unordered_set<const void*> attr_done;
 };
+// true if `fn` was already configured on ctx's device; otherwise records it and returns false
+static inline bool fx_attr_once(fx_ctx* ctx, const void* fn) { return !ctx->attr_done.insert(fn).second; }
+constexpr int FX_MAX_DYN_SMEM = 227 * 1024;
 
 // Arena: reserve() guarantees capacity (may re-allocate: only legal when nothing is live),
 // alloc() bumps.  All sizes rounded to 256 B.
@@ -125,7 +132,13 @@ struct fx_model {
     double* W = nullptr;       // [k_pad][n_ld] components (column-major n_ld x k_pad)
     double* bias = nullptr;    // [k_pad]  r'W  (zero when not centred)
     double* colmean = nullptr; // [n_ld]
+    double* wsum = nullptr;    // [k_pad]  1'W (sum over the n training rows of every component)
     double grandmean = 0.0;
+    // 1 when some component is not orthogonal to the constant vector (|1'w| above rounding level):
+    // the transform then applies the full double-centring formula with the per-query row mean
+    // (SURVEY.md A.2); for eigenvectors of the centred matrix with non-zero eigenvalue 1'w = 0 and
+    // the k-vector bias alone is exact.
+    int need_rowmean = 0;
 };
 
 // ------------------------------------------------------------------------------------------

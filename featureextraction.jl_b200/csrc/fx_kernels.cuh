@@ -112,6 +112,10 @@ int fx_launch_T_restart(fx_ctx* ctx, double* T, int ldt, int tsize, const double
 // bias[c] = sum_j colmean[j] * W[c][j]
 int fx_launch_bias(fx_ctx* ctx, const double* colmean, const double* W, int64_t ld, int64_t n,
                    int k, double* bias);
+// sums[c] = sum_j W[c][j], sums[k + c] = sum_j |W[c][j]|   (j < n)
+int fx_launch_colsums(fx_ctx* ctx, const double* W, int64_t ld, int64_t n, int k, double* sums);
+// Fills m->wsum / m->need_rowmean from m->W (synchronises the stream).
+int fx_model_finish_centering(fx_ctx* ctx, fx_model* m);
 
 // ---- transform.cu ------------------------------------------------------------------------
 // out[c][q] = sum_j map(Z_q . X_j) W[c][j] - bias[c]
@@ -123,6 +127,10 @@ struct TransformArgs {
     const double* bias;                                // [kcols] or null
     double* out; int64_t ldo;                          // [kcols][ldo] (column-major m_pad x kcols)
     int kernel_id; double kp[3];
+    // exact double centring for components not orthogonal to 1: out -= (rowmean_q - grand) wsum[c]
+    const double* wsum = nullptr;                      // [kcols] 1'W or null
+    double grand = 0.0;                                // grand mean of the training kernel matrix
+    double* rz_out = nullptr;                          // [m_pad] raw row sums of k(Z, X) or null
 };
 int fx_launch_transform(fx_ctx* ctx, const TransformArgs& a, int variant);
 

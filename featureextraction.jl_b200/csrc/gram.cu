@@ -412,8 +412,7 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     }
     if (a.rows_pad == 0 || a.ldk == 0) return 0;
     if (variant == 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!fx_attr_once(ctx, (const void*)gram_dmma_kernel<0>)) {
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -421,7 +420,6 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            attr_set = true;
         }
         long want = 2L * (ctx->sm_count > 0 ? ctx->sm_count : 148);
         const unsigned grid = (unsigned)(p.tiles_total < want ? p.tiles_total : want);

@@ -335,6 +335,16 @@ __global__ void bias_kernel(const double* colmean, const double* W, long ld, lon
     if (threadIdx.x == 0) bias[c] = s;
 }
 
+__global__ void colsums_kernel(const double* W, long ld, long n, int k, double* sums) {
+    __shared__ double red[33];
+    const int c = blockIdx.x;
+    double s = 0.0, a = 0.0;
+    for (long j = threadIdx.x; j < n; j += blockDim.x) { const double w = W[(long)c * ld + j]; s += w; a += fabs(w); }
+    s = block_sum(s, red);
+    a = block_sum(a, red);
+    if (threadIdx.x == 0) { sums[c] = s; sums[k + c] = a; }
+}
+
 }  // namespace
 
 size_t fx_jacobi_work_doubles(int m) { return (size_t)m * m; }
@@ -353,11 +363,9 @@ int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int l
     int nwarps = (half + per - 1) / per;
     if (nwarps < 2) nwarps = 2;
     const int threads = 32 * nwarps;
-    static size_t smem_set[3] = {0, 0, 0};
-    if (smem > smem_set[mode]) {
-        if (mode == 2) FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (mode == 1) FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[mode] = smem;
+    if (!fx_attr_once(ctx, (const void*)jacobi_kernel<true, true>)) {
+        FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_MAX_DYN_SMEM));
+        FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_MAX_DYN_SMEM));
     }
     if (mode == 2) jacobi_kernel<true, true><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40, need);
     else if (mode == 1) jacobi_kernel<true, false><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40, need);
@@ -384,11 +392,8 @@ int fx_launch_chol_factors(fx_ctx* ctx, const double* G, int ldg, int b, double 
         return FX_ERR_CUDA;
     }
     const size_t smem = (2 * 64 * 65 + 64) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
+    if (!fx_attr_once(ctx, (const void*)chol_factors_kernel))
         FX_CUDA(cudaFuncSetAttribute(chol_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
     chol_factors_kernel<<<1, 256, smem, ctx->stream>>>(G, ldg, b, thr, M, Cfac, need_svqb, ndef);
     ctx->launches++;
     FX_LAUNCH_CHECK();
@@ -444,6 +449,14 @@ int fx_launch_bias(fx_ctx* ctx, const double* colmean, const double* W, int64_t 
                    int k, double* bias) {
     if (k <= 0) return 0;
     bias_kernel<<<k, 256, 0, ctx->stream>>>(colmean, W, ld, n, k, bias);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_colsums(fx_ctx* ctx, const double* W, int64_t ld, int64_t n, int k, double* sums) {
+    if (k <= 0) return 0;
+    colsums_kernel<<<k, 256, 0, ctx->stream>>>(W, ld, n, k, sums);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;

@@ -275,11 +275,8 @@ int launch_nb(fx_ctx* ctx, const CUtensorMap& tmK, const CUtensorMap& tmV, SymmP
     if (ns > 4) ns = 4;
     p.nstage = ns;
     const int smem = ns * STAGE_BYTES + 1024 + 128;
-    static int smem_set = 0;
-    if (smem > smem_set) {
+    if (!fx_attr_once(ctx, (const void*)symm_dmma_kernel<NB, CENTER>))
         FX_CUDA(cudaFuncSetAttribute(symm_dmma_kernel<NB, CENTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
-    }
     const unsigned grid = (unsigned)((p.rows_pad / RT) * p.splits);
     symm_dmma_kernel<NB, CENTER><<<grid, CENTER ? 320 : 288, smem, ctx->stream>>>(tmK, tmV, p);
     ctx->launches++;

@@ -16,6 +16,9 @@
 namespace {
 
 constexpr int TQ = 128, TN = 64, TBK = 16, TST = 4;
+// Row pitches (doubles) of the staged slabs, chosen for conflict-free fragment loads: Z rows are
+// read 16 bytes at a time at kr*ZS + 2g (kr = 4kk + t; a quarter-warp is g in {2h, 2h+1} x t = 0..3,
+// so ZS/2 = 2 (mod 8) gives 8 distinct 16-byte units), X rows 8 bytes at a time at kr*XS + 8nt + g.
 constexpr int ZS = TQ + 4, XS = TN + 4, WS = 72;
 constexpr int TSTAGE_D = TBK * ZS + TBK * XS;            // 3200 doubles
 
@@ -24,11 +27,57 @@ struct TrParams {
     const double* Xp; long ldx; const double* nx;
     const double* W; long ldw;
     const double* bias;
-    double* out; long ldo;          // [nsplit][kc][ldo] when nsplit > 1 (bias applied in the reduce)
+    double* out; long ldo;          // [nsplit][kc + 1][ldo] when nsplit > 1 (bias applied in the reduce;
+                                    // the extra column carries the partial row sums of k(Z, X))
     long n_valid;
     int kt, ntiles, nsplit, kc;
+    // Exact double centring for components that are not orthogonal to 1:
+    //   out -= (rowmean_q - grand) * wsum[c],  rowmean_q = (1/n) sum_j k(z_q, x_j).
+    // want_rz != 0 makes the MMA warps accumulate the row sums of the mapped tile.
+    int want_rz;
+    const double* wsum;             // [kc] 1'W, or null (no correction applied)
+    double grand, inv_n;
+    double* rz_out;                 // [m_pad] raw row sums of k(Z, X), or null
     KernelMap km;
 };
+
+// Kernel map of one warp's 16 x 64 slice of the cross kernel tile, in registers.  Interior tiles
+// run the bare arithmetic (no predicates: the compiler otherwise wraps every element in its own
+// branch region and the 32 maps of a thread run back to back instead of interleaved); the last
+// tile of a ragged training set masks the padding columns.
+// Accumulator (nt, q) of thread (g, t) is training column j0 + 8 nt + 2t + q.
+template <int KID, bool EDGE>
+__device__ __forceinline__ void transform_map(const KernelMap& km, double (&acc1)[2][8][2], const double (&nzs)[2],
+                                              const double* __restrict__ nxt, long j0, long n_valid, int t,
+                                              bool want_rz, double (&rz)[2]) {
+    const double two_g = 2.0 * km.p0, neg_g = -km.p0;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        double nx[2] = {0.0, 0.0};
+        if (KID == 0) {
+            const double2 v = *reinterpret_cast<const double2*>(nxt + nt * 8 + 2 * t);
+            nx[0] = v.x; nx[1] = v.y;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const long j = j0 + nt * 8 + 2 * t + q;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                double v;
+                if (KID == 0) {
+                    // exp(-gamma (|z|^2 + |x|^2 - 2 z'x)), norms folded in with two FMAs
+                    v = fx_exp_nonpos(fma(two_g, acc1[mt][nt][q], fma(neg_g, nx[q], nzs[mt])));
+                } else {
+                    v = kernel_map_t<KID>(km, acc1[mt][nt][q], 0.0, 0.0, false);
+                }
+                if (EDGE) v = (j < n_valid) ? v : 0.0;
+                acc1[mt][nt][q] = v;
+                if (want_rz) rz[mt] += v;
+            }
+        }
+    }
+}
+
 
 template <int NBK, int KID>
 __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
@@ -92,11 +141,14 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
 #pragma unroll
         for (int nk = 0; nk < NBK; ++nk) acc2[mt][nk][0] = acc2[mt][nk][1] = 0.0;
     constexpr bool gauss = (KID == 0);
-    double nzr[2] = {0.0, 0.0};
+    // Row mapping: accumulator row (mt, g) is query q0 + warp*16 + 2g + mt (one 16-byte load per
+    // k-step feeds both MMA row blocks).
+    double nzs[2] = {0.0, 0.0}, rz[2] = {0.0, 0.0};
     if (gauss) {
-        nzr[0] = p.nz[q0 + warp * 16 + g];
-        nzr[1] = p.nz[q0 + warp * 16 + 8 + g];
+        nzs[0] = -p.km.p0 * p.nz[q0 + warp * 16 + 2 * g];
+        nzs[1] = -p.km.p0 * p.nz[q0 + warp * 16 + 2 * g + 1];
     }
+    const bool want_rz = p.want_rz != 0;
 
     int it = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -110,14 +162,16 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
         for (int kt = 0; kt < KT; ++kt, ++it) {
             const int s = it % TST;
             mbar_wait(&full[s], (it / TST) & 1);
-            const double* Zs = smem + (size_t)s * TSTAGE_D + warp * 16 + g;
+            const double* Zs = smem + (size_t)s * TSTAGE_D + warp * 16 + 2 * g;
             const double* Xs = smem + (size_t)s * TSTAGE_D + TBK * ZS + g;
 #pragma unroll
             for (int kk = 0; kk < TBK / 4; ++kk) {
                 const int kr = kk * 4 + t;
                 double a[2], b[8];
-                a[0] = Zs[kr * ZS];
-                a[1] = Zs[kr * ZS + 8];
+                {
+                    const double2 v = *reinterpret_cast<const double2*>(Zs + kr * ZS);
+                    a[0] = v.x; a[1] = v.y;
+                }
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) b[nt] = Xs[kr * XS + nt * 8];
 #pragma unroll
@@ -132,23 +186,11 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
         // kernel map in registers (the tile's W slab and norms were staged by the producer)
         const int wi = tile - t_begin, ws = wi & 1;
         mbar_wait(&wfull[ws], (wi >> 1) & 1);
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const long j = j0 + nt * 8 + 2 * t;
-            double nx0 = 0.0, nx1 = 0.0;
-            if (gauss) {
-                const double2 v = *reinterpret_cast<const double2*>(nxs + ws * TN + nt * 8 + 2 * t);
-                nx0 = v.x; nx1 = v.y;
-            }
-            const bool v0 = j < p.n_valid, v1 = (j + 1) < p.n_valid;
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                acc1[mt][nt][0] = v0 ? kernel_map_t<KID>(p.km, acc1[mt][nt][0], nzr[mt], nx0, false) : 0.0;
-                acc1[mt][nt][1] = v1 ? kernel_map_t<KID>(p.km, acc1[mt][nt][1], nzr[mt], nx1, false) : 0.0;
-            }
-        }
+        if (j0 + TN <= p.n_valid) transform_map<KID, false>(p.km, acc1, nzs, nxs + ws * TN, j0, p.n_valid, t, want_rz, rz);
+        else                      transform_map<KID, true>(p.km, acc1, nzs, nxs + ws * TN, j0, p.n_valid, t, want_rz, rz);
 
-        // second contraction: acc2 += Ktile (16 x 64 per warp) * W[j0:j0+64, :]
+        // second contraction: acc2 += Ktile (16 x 64 per warp) * W[j0:j0+64, :]; the C fragments of the
+        // first MMA are the A fragments of the second (k index t <-> tile column 8 nt + 2t + q)
         const double* Wt = Wsm + (size_t)ws * NBK * 8 * WS + g * WS + 2 * t;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -166,53 +208,88 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
         if (lane == 0) mbar_arrive(&wempty[ws]);
     }
 
-    double* out = p.out + (long)sp * p.kc * p.ldo;
+    // row sums of k(Z, X) over this split: reduce the four t-lanes of a row
+    if (want_rz) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt) {
+            rz[mt] += __shfl_xor_sync(0xffffffffu, rz[mt], 1);
+            rz[mt] += __shfl_xor_sync(0xffffffffu, rz[mt], 2);
+        }
+    }
+    const bool split = p.nsplit > 1;
+    double* out = p.out + (long)sp * (split ? p.kc + 1 : p.kc) * p.ldo;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const long row = q0 + warp * 16 + 2 * g + mt;
+        double corr = 0.0;                       // (rowmean - grand), applied with wsum below
+        if (want_rz) {
+            if (split) { if (t == 0) out[(long)p.kc * p.ldo + row] = rz[mt]; }
+            else {
+                if (p.rz_out && t == 0) p.rz_out[row] = rz[mt];
+                corr = rz[mt] * p.inv_n - p.grand;
+            }
+        }
 #pragma unroll
         for (int nk = 0; nk < NBK; ++nk) {
-            const long row = q0 + warp * 16 + mt * 8 + g;
             const int c = nk * 8 + 2 * t;
             double b0 = 0.0, b1 = 0.0;
-            if (p.nsplit == 1 && p.bias) { b0 = p.bias[c]; b1 = p.bias[c + 1]; }
+            if (!split) {
+                if (p.bias) { b0 = p.bias[c]; b1 = p.bias[c + 1]; }
+                if (p.wsum) { b0 = fma(corr, p.wsum[c], b0); b1 = fma(corr, p.wsum[c + 1], b1); }
+            }
             out[(long)c * p.ldo + row] = acc2[mt][nk][0] - b0;
             out[(long)(c + 1) * p.ldo + row] = acc2[mt][nk][1] - b1;
         }
+    }
 }
 
-__global__ void transform_reduce_kernel(const double* part, int nsplit, int kc, long ldo,
-                                        const double* bias, double* out) {
+// one thread per query: sums the split partials in a fixed order, applies bias and the row-mean term
+__global__ void transform_reduce_kernel(const double* part, int nsplit, int kc, long ldo, const double* bias,
+                                        int want_rz, const double* wsum, double grand, double inv_n,
+                                        double* rz_out, double* out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y;
     if (i >= ldo) return;
-    double s = 0.0;
-    for (int k = 0; k < nsplit; ++k) s += part[((long)k * kc + c) * ldo + i];
-    out[(long)c * ldo + i] = s - (bias ? bias[c] : 0.0);
+    double corr = 0.0;
+    if (want_rz) {
+        double r = 0.0;
+        for (int k = 0; k < nsplit; ++k) r += part[((long)k * (kc + 1) + kc) * ldo + i];
+        if (rz_out) rz_out[i] = r;
+        corr = r * inv_n - grand;
+    }
+    for (int c = 0; c < kc; ++c) {
+        double s = 0.0;
+        for (int k = 0; k < nsplit; ++k) s += part[((long)k * (kc + 1) + c) * ldo + i];
+        double b = bias ? bias[c] : 0.0;
+        if (wsum) b = fma(corr, wsum[c], b);
+        out[(long)c * ldo + i] = s - b;
+    }
 }
 
 __global__ void transform_naive_kernel(const TrParams p, int d_pad, long m_pad) {
     const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (q >= m_pad) return;
-    double s = 0.0;
+    double s = 0.0, rsum = 0.0;
     for (long j = 0; j < p.n_valid; ++j) {
         double dot = 0.0;
         for (int f = 0; f < d_pad; ++f) dot += p.Zp[(long)f * p.ldz + q] * p.Xp[(long)f * p.ldx + j];
         const double ni = (p.km.id == FX_KERNEL_GAUSSIAN) ? p.nz[q] : 0.0;
         const double nj = (p.km.id == FX_KERNEL_GAUSSIAN) ? p.nx[j] : 0.0;
-        s += kernel_map(p.km, dot, ni, nj, false) * p.W[(long)c * p.ldw + j];
+        const double kv = kernel_map(p.km, dot, ni, nj, false);
+        s += kv * p.W[(long)c * p.ldw + j];
+        rsum += kv;
     }
-    p.out[(long)c * p.ldo + q] = s - (p.bias ? p.bias[c] : 0.0);
+    double b = p.bias ? p.bias[c] : 0.0;
+    if (p.want_rz && p.wsum) b += (rsum * p.inv_n - p.grand) * p.wsum[c];
+    if (p.want_rz && p.rz_out && c == 0) p.rz_out[q] = rsum;
+    p.out[(long)c * p.ldo + q] = s - b;
 }
 
 template <int NBK, int KID>
 int launch_tr2(fx_ctx* ctx, const TrParams& p, long m_pad) {
     constexpr int SMEM = (TST * TSTAGE_D + 2 * NBK * 8 * WS + 2 * TN) * 8 + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!fx_attr_once(ctx, (const void*)transform_kernel<NBK, KID>)) 
         FX_CUDA(cudaFuncSetAttribute(transform_kernel<NBK, KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
     dim3 grid((unsigned)(m_pad / TQ), (unsigned)p.nsplit);
     transform_kernel<NBK, KID><<<grid, 288, SMEM, ctx->stream>>>(p);
     ctx->launches++;
@@ -243,7 +320,7 @@ size_t fx_transform_scratch(fx_ctx* ctx, int64_t m_pad, int64_t n_ld, int kc, in
     if (ns < 1) ns = 1;
     if (ns > 64) ns = 64;
     if (nsplit_out) *nsplit_out = (int)ns;
-    return ns > 1 ? (size_t)ns * kc * m_pad : 0;
+    return ns > 1 ? (size_t)ns * (kc + 1) * m_pad : 0;      // + 1: partial row sums of k(Z, X)
 }
 
 int fx_launch_transform_ex(fx_ctx* ctx, const TransformArgs& a, int variant, double* scratch, int nsplit) {
@@ -257,6 +334,8 @@ int fx_launch_transform_ex(fx_ctx* ctx, const TransformArgs& a, int variant, dou
     p.Zp = a.Zp; p.ldz = a.ldz; p.nz = a.nz; p.Xp = a.Xp; p.ldx = a.ldx; p.nx = a.nx;
     p.W = a.W; p.ldw = a.ldw; p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.n_valid = a.n_valid;
     p.kt = (int)(a.d_pad / TBK); p.ntiles = (int)(a.n_ld / TN); p.nsplit = 1; p.kc = a.kcols;
+    p.want_rz = (a.wsum || a.rz_out) ? 1 : 0; p.wsum = a.wsum; p.grand = a.grand; p.rz_out = a.rz_out;
+    p.inv_n = a.n_valid > 0 ? 1.0 / (double)a.n_valid : 0.0;
     p.km.id = a.kernel_id; p.km.p0 = a.kp[0]; p.km.p1 = a.kp[1]; p.km.p2 = a.kp[2];
     double tmp[3];
     if (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp)) { fx_set_error("fx_launch_transform_ex: invalid argument 1 (fx_make_kernel_map(a.kernel_id, a.kp, &p.km.ipow, tmp))"); return -1; }
@@ -282,8 +361,8 @@ int fx_launch_transform_ex(fx_ctx* ctx, const TransformArgs& a, int variant, dou
         default: FX_TRY(launch_tr<8>(ctx, p, a.m_pad)); break;
     }
     if (p.nsplit > 1) {
-        dim3 grid((unsigned)ceil_div(a.ldo, 256), (unsigned)a.kcols);
-        transform_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(scratch, p.nsplit, a.kcols, a.ldo, a.bias, a.out);
+        transform_reduce_kernel<<<(unsigned)ceil_div(a.ldo, 128), 128, 0, ctx->stream>>>(
+            scratch, p.nsplit, a.kcols, a.ldo, a.bias, p.want_rz, p.wsum, p.grand, p.inv_n, p.rz_out, a.out);
         ctx->launches++;
         FX_LAUNCH_CHECK();
     }

@@ -124,7 +124,10 @@ int fx_kpca_fit_dev_f64(fx_ctx* ctx, const double* dX, int64_t n, int64_t d, int
                         double alpha, double eps, const fx_solver_opts* opts,
                         double* dV, int64_t ldv, double* dlambda,
                         fx_model** model, fx_stats* stats);
-/* out: m x k = k(Z,X) W - 1 (r'W)   (== full double-centring formula when 1'W = 0). */
+/* out: m x k = (k(Z,X) - 1 r' - r_z 1' + mu) W  (full double-centring formula).  For
+ * components orthogonal to 1 (every eigenvector of the centred matrix with non-zero eigenvalue)
+ * this is k(Z,X) W - 1 (r'W) and only the k-vector bias is applied; otherwise the kernel also
+ * accumulates the per-query row means r_z.  Any k (launches of <= 64 components). */
 int fx_kpca_transform_f64(fx_ctx* ctx, const fx_model* model, const double* Z, int64_t m,
                           int64_t ldz, double* out, int64_t ldo, fx_stats* stats);
 int fx_kpca_transform_dev_f64(fx_ctx* ctx, const fx_model* model, const double* dZ, int64_t m,
@@ -178,6 +181,12 @@ int fx_center_f64(fx_ctx* ctx, double* K, int64_t n, int64_t ldk,
 int fx_symm_f64(fx_ctx* ctx, const double* K, int64_t n, int64_t ldk,
                 const double* V, int b, int64_t ldv, double* Y, int64_t ldy,
                 int variant, fx_stats* stats);
+/* The centring pass as a FIT runs it: K (n x n symmetric, host) is centred in place by the fused
+ * kernel that also multiplies, Y (n x b) = K~ V.  Same result as fx_center_f64 + fx_symm_f64;
+ * exposed so that the fused write-back is tested element by element (kpca.jl:52). */
+int fx_center_symm_f64(fx_ctx* ctx, double* K, int64_t n, int64_t ldk, const double* V, int b,
+                       int64_t ldv, double* Y, int64_t ldy, double* colmean, double* grandmean,
+                       fx_stats* stats);
 /* Device Jacobi eigensolver: A (m x m symmetric) -> w descending, A overwritten by
  * eigenvectors (columns).  m <= 1024. */
 int fx_syevd_small_f64(fx_ctx* ctx, double* A, int m, int64_t lda, double* w, int* sweeps);
