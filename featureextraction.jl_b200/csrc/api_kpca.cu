@@ -144,7 +144,7 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
         // column sums == row sums (K symmetric): local rows, then all-gather
         double* rs_loc = g.rowsum + g.row0;
         tm.begin(&st->center_ms);
-        FX_TRY(fx_launch_rowpart_reduce(ctx, g.rowpart, g.n_ld / 64, g.ld, rs_loc));
+        FX_TRY(fx_launch_rowpart_reduce(ctx, g.rowpart, fx_gram_rowpart_slots(g.n_ld), g.ld, rs_loc));
         tm.end();
         if (ctx->world > 1) {
             tm.begin(&st->comm_ms);

@@ -84,8 +84,15 @@ struct fx_ctx {
     // per device / context, so the registry lives here and not in a process-wide static)
     std::unordered_set<const void*> attr_done;
 };
-// true if `fn` was already configured on ctx's device; otherwise records it and returns false
-static inline bool fx_attr_once(fx_ctx* ctx, const void* fn) { return !ctx->attr_done.insert(fn).second; }
+// Opt a kernel into `bytes` of dynamic shared memory once per context (recorded only on success).
+// Pass template instantiations in parentheses: FX_SET_SMEM_ONCE(ctx, (kernel<1, 2>), bytes).
+#define FX_SET_SMEM_ONCE(ctx, fn, bytes)                                                               \
+    do {                                                                                               \
+        if (!(ctx)->attr_done.count((const void*)(fn))) {                                              \
+            FX_CUDA(cudaFuncSetAttribute((fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            (ctx)->attr_done.insert((const void*)(fn));                                                \
+        }                                                                                              \
+    } while (0)
 constexpr int FX_MAX_DYN_SMEM = 227 * 1024;
 
 // Arena: reserve() guarantees capacity (may re-allocate: only legal when nothing is live),

@@ -14,7 +14,7 @@ struct GramArgs {
     int64_t rows_pad;                   // multiple of 128
     int64_t rows_valid, cols_valid;     // entries outside are written as 0
     int64_t diag_shift;                 // global index of local row 0 (symmetric case), else -1
-    double* rowpart;                    // [ldk/64][rows_pad] per-tile partial row sums or null
+    double* rowpart;                    // [fx_gram_rowpart_slots(ldk)][rows_pad] per-tile partial row sums or null
     int kernel_id; double kp[3];
     int sym_source = 0;                 // 1: A is the row block [diag_shift, +rows_pad) of B (K symmetric)
     int no_symmetry = 0;                // 1: compute every tile even when the matrix is symmetric
@@ -30,6 +30,8 @@ struct GramArgs {
 int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, int64_t d_pad,
                        double* norms);
 int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant);
+// slots of GramArgs::rowpart per row: one partial row sum per 128-column output tile
+int64_t fx_gram_rowpart_slots(int64_t ldk);
 
 // ---- center.cu -------------------------------------------------------------------------
 // rowsum[i] = sum over tiles of rowpart[t][i]

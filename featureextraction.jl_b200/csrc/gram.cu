@@ -1,46 +1,68 @@
 // gram.cu -- kernel-matrix construction: K = map(A B') with the kernel map, zero padding and
-// per-tile row sums fused into the epilogue.  Replaces MLKernels.kernelmatrix as called at
+// per-tile row sums fused behind the contraction.  Replaces MLKernels.kernelmatrix as called at
 // /root/reference/src/kpca.jl:51 (symmetric) and kpca.jl:65 (cross).
 //
-// Data path (persistent CTAs, 2 per SM, each looping over 128x64 output tiles):
-//   producer warpgroup (one active warp; gives its registers to the MMA warps via setmaxnreg):
-//     HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 3-stage smem ring of
-//     16-feature slabs; it runs ahead across tile boundaries, so the next tile's first slabs
-//     land while the MMA warps are still in the epilogue of the previous one
-//   4 MMA warps: LDS.64 conflict-free (row stride = 4 mod 16 doubles) --> DMMA.8x8x4
-//     (mma.sync f64), 64x32 register tile per warp, no CTA-wide barrier in the main loop
-//   epilogue: kernel map applied IN REGISTERS (64 independent elements per thread, branch-free
-//     exp) --> row sums by 2-step warp shuffle --> 16-byte stores straight from the accumulator
-//     fragments (one store instruction covers 8 rows x 64 contiguous bytes = 16 full sectors).
+// One persistent CTA per SM, warp-specialised (512 threads, setmaxnreg 200 / 88 / 24):
+//   producer (warp 12, one lane): per 8-feature step TWO tensor-map bulk copies (TMA, SASS UTMALDG),
+//     boxes of {132 observations x 8 features} of the row and of the column operand -- the box is 4
+//     elements wider than the 128 it feeds, which makes the shared-memory row pitch 132 doubles and
+//     the LDS.64 fragment reads conflict free (t*132 + g distinct mod 16) -- into a 5-stage ring
+//     guarded by mbarrier full/empty pairs; it runs ahead across tile boundaries.
+//   8 MMA warps (2 x 4, 64 x 32 register tile each, DMMA.8x8x4 = mma.sync f64): main loop only.
+//     When a 128 x 128 tile is done they drop the RAW dot products into a 128 KB staging tile in
+//     shared memory (the layout a 128-byte-swizzled TMA store expects) and start the next tile at
+//     once -- the kernel map never stops the DMMA stream of an SM.
+//   4 epilogue warps (one thread per tile row): kernel map in place in the staging tile (branch-free
+//     exp / templated powers / tanh), row sums, then ONE tensor-map bulk store (UTMASTG) of the
+//     tile to K.  In round 1 the map ran inside the MMA warps and cost 20-30 % of the kernel.
 //
 // Symmetry.  K is symmetric when A is a row block of B.  sym = 1 (one rank, or no peer access):
 // inside this rank's square diagonal block only the tiles on / right of the diagonal are computed
-// and the strictly-right ones are mirrored by transposed stores from the fragments.  sym = 2
-// (several ranks, peer arenas mapped through CUDA IPC): the off-diagonal blocks are shared out
-// too -- of each pair of blocks (r,c) / (c,r) exactly one rank computes every 128x128 super-tile
-// and stores the transposed values, and the column sums that are the peer's row-sum partials,
-// STRAIGHT INTO THE PEER'S K over NVLink (plain st.global to the IPC-mapped address), so every
-// rank executes ~half of its row block and no separate exchange step exists.
+// and the strictly-right ones are mirrored: the epilogue thread that owns tile row r writes its
+// mapped values down column r of the transposed tile, so a warp's store instruction covers 32
+// consecutive doubles (256 contiguous bytes) of one row of the mirrored tile.  sym = 2 (several
+// ranks, peer arenas mapped through CUDA IPC): the off-diagonal blocks are shared out too -- of
+// each pair of blocks (r,c) / (c,r) exactly one rank computes every tile and stores the transposed
+// values, and the column sums that are the peer's row-sum partials, STRAIGHT INTO THE PEER'S K
+// over NVLink (st.global to the IPC-mapped address), so every rank executes ~half of its row
+// block and no separate exchange step exists.
+#include <cuda.h>
+#include <stdlib.h>
 #include "fx_kernels.cuh"
 #include "gram_tiles.cuh"
 
+int fx_launch_gram_v3(fx_ctx* ctx, const GramArgs& a, int variant);      // gram_v3.cu
+
 namespace {
 
-constexpr int BM = FX_GRAM_BM, BN = FX_GRAM_BN, BK = 16, STAGES = 3;
-constexpr int AS = BM + 4;                      // 132: (t*AS + g) mod 16 distinct for t,g in 0..3
-constexpr int BS = BN + 4;                      // 68
-constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25600 B)
-// mirror staging: per MMA warp two buffers of 8 transposed rows x 64 (+2 pad: conflict-free
-// 8-byte stores for lanes (g,t) -> word (2t+q)*TS + g) -- sent off with 512-byte bulk stores
-constexpr int TS = 66, TBUF_D = 8 * TS;
-constexpr int SMEM_BYTES = STAGES * STAGE_D * 8 + 2 * 2 * BM * 8 + 128 + 4 * 2 * TBUF_D * 8;
+constexpr int BM = FX_GRAM_BM, BN = FX_GRAM_BN, BK = 8, NST = 5;
+constexpr int PITCH = 132;                                   // doubles per staged operand row
+constexpr int SLAB_BYTES = BK * PITCH * 8;                   // 8448 (multiple of 128)
+constexpr int STAGE_BYTES = 2 * SLAB_BYTES;
+constexpr int ACC_BYTES = BM * BN * 8;                       // 131072: the staging tile
+constexpr int OFF_STAGES = ACC_BYTES;
+constexpr int OFF_COLN = OFF_STAGES + NST * STAGE_BYTES;
+constexpr int OFF_BARS = OFF_COLN + BN * 8;
+constexpr int SMEM_BYTES = OFF_BARS + 128 + 1024;            // + slack for the 1024-byte alignment
+constexpr int NTHREADS = 512;
+constexpr int EPI_THREADS = 128, EPI_TID0 = 256;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 
-// 1-D bulk store shared -> global (TMA engine); the destination may be a peer GPU's memory
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                     __cvta_generic_to_global(dst_gmem)),
-                 "r"(smem_u32(src_smem)), "r"(bytes)
-                 : "memory");
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
 }
 
 struct GramParams {
@@ -61,7 +83,28 @@ struct GramParams {
 
 // tile_role() / tile_coords(): gram_tiles.cuh (host-testable)
 
-__device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar,
+                                            uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2,
+                                             uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(
+            reinterpret_cast<uint64_t>(tm)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Byte offset of the 16-byte unit that holds columns (2u', 2u'+1) of chunk `c` in row `r` of the
+// staging tile: [chunk of 16 columns][row][128 bytes], the eight 16-byte units of a row XOR-swizzled
+// with (row & 7) -- the shared-memory image of a {16, 128, 8} box of a SWIZZLE_128B tensor map.
+__device__ __forceinline__ int stage_off(int r, int c, int u) { return c * (BM * 128) + r * 128 + ((u ^ (r & 7)) << 4); }
 
 // Map of one element; for the Gaussian kernel (KID 0) the norms arrive pre-scaled by -gamma.
 template <int KID>
@@ -70,165 +113,82 @@ __device__ __forceinline__ double gram_map(const KernelMap& km, double dot, doub
     return kernel_map_t<KID>(km, dot, ni, nj, same);
 }
 
-// Kernel map + row sums + stores for one warp's 64x32 accumulator tile.  EDGE tiles (ragged
-// borders or touching the diagonal) carry the validity masks and the same-point test; interior
-// tiles run the bare arithmetic.
-template <int KID, bool EDGE>
-__device__ __forceinline__ void gram_epilogue_plain(const GramParams& p, double (&acc)[8][4][2],
-                                                    const double (&ni)[8], const double (&nbv)[4][2], long i0,
-                                                    long j0, int wm, int wn, int g, int t, double* rsb) {
-    const long jb = j0 + wn * 32 + 2 * t;
+// Epilogue pass over one tile row (thread e owns row e of the staging tile): map in place, row sum,
+// and -- for MIRROR tiles -- the transposed stores into the owner's K.  EDGE tiles (ragged borders
+// or touching the diagonal) carry the validity masks and the same-point test.
+template <int KID, bool EDGE, bool MIRROR>
+__device__ __forceinline__ double gram_epilogue_row(const GramParams& p, unsigned char* S, const double* coln,
+                                                    int e, long i0, long j0, double ni, double* mir) {
+    const long i = i0 + e;
+    const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+    const bool iv = i < p.rows_valid;
+    double rsum = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 16; ++c) {
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt) {
-        const long i = i0 + wm * 64 + mt * 8 + g;
-        double* krow = p.K + i * p.ldk + jb;
-        const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
-        const bool iv = i < p.rows_valid;
-        double sacc = 0.0;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int u = 0; u < 8; ++u) {
+            double2* ptr = reinterpret_cast<double2*>(S + stage_off(e, c, u));
+            const double2 dv = *ptr;
+            const int col = c * 16 + u * 2;
+            double n0 = 0.0, n1 = 0.0;
+            if (KID == 0) {
+                const double2 nn = *reinterpret_cast<const double2*>(coln + col);     // broadcast read
+                n0 = nn.x; n1 = nn.y;
+            }
             double v0, v1;
             if (EDGE) {
-                const long j = jb + nt * 8;
-                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], ig == j);
-                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], ig == j + 1);
+                const long j = j0 + col;
+                v0 = gram_map<KID>(p.km, dv.x, ni, n0, ig == j);
+                v1 = gram_map<KID>(p.km, dv.y, ni, n1, ig == j + 1);
                 v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
                 v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
             } else {
-                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], false);
-                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], false);
+                v0 = gram_map<KID>(p.km, dv.x, ni, n0, false);
+                v1 = gram_map<KID>(p.km, dv.y, ni, n1, false);
             }
-            *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(v0, v1);
-            sacc += v0 + v1;
-        }
-        if (p.rowpart) {
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-            if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = sacc;
-        }
-    }
-}
-
-// The same for MIRROR tiles (symmetric mode): also sends the transposed tile to its owner.
-template <int KID, bool EDGE>
-__device__ __forceinline__ void gram_epilogue_mirror(const GramParams& p, double (&acc)[8][4][2],
-                                              const double (&ni)[8], long i0,
-                                              long j0, int wm, int wn, int g, int t, double* rsb,
-                                              double* Kmir, double* rpmir, long mir_row0, double* tbuf) {
-    // Kmir / rpmir: K and rowpart of the rank that owns rows [mir_row0, +rows_pad) -- this rank
-    // itself inside the diagonal block, a peer (NVLink) for the shared-out blocks.  The mirrored
-    // values go through a small transposed staging buffer (tbuf: 2 x [8][TS] per warp) and leave
-    // as 512-byte bulk stores, 8 per 8-column group: direct transposed stores from the fragments
-    // are 64-byte pieces, which NVLink carries at a fraction of its bandwidth.
-    const long jb = j0 + wn * 32 + 2 * t;
-    const int lane = g * 4 + t;
-    double sacc[8];
-#pragma unroll
-    for (int mt = 0; mt < 8; ++mt) sacc[mt] = 0.0;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        double* tb = tbuf + (nt & 1) * TBUF_D;
-        double cs0 = 0.0, cs1 = 0.0;
-        // column norms re-read per group (L1 hit): keeps 12 registers free for the row sums
-        double nb0 = 0.0, nb1 = 0.0;
-        if (KID == 0) {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(p.nb + jb + nt * 8));
-            nb0 = -p.km.p0 * v.x; nb1 = -p.km.p0 * v.y;
-        }
-        if (nt >= 2) {
-            // the bulk stores issued from this buffer two groups ago must have read it
-            if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-        }
-#pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
-            const long i = i0 + wm * 64 + mt * 8 + g;
-            double v0, v1;
-            if (EDGE) {
-                const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
-                const bool iv = i < p.rows_valid;
-                const long j = jb + nt * 8;
-                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, ig == j);
-                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, ig == j + 1);
-                v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
-                v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
-            } else {
-                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, false);
-                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, false);
-            }
-            *reinterpret_cast<double2*>(p.K + i * p.ldk + jb + nt * 8) = make_double2(v0, v1);
-            tb[(2 * t) * TS + mt * 8 + g] = v0;              // transposed: row = column of the tile
-            tb[(2 * t + 1) * TS + mt * 8 + g] = v1;
-            cs0 += v0;
-            cs1 += v1;
-            sacc[mt] += v0 + v1;
-        }
-        {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane < 8) {
-                // transposed row j = j0 + wn*32 + nt*8 + lane, columns [i0 + wm*64, +64) of the owner's block
-                double* dst = Kmir + (j0 + wn * 32 + nt * 8 + lane - mir_row0) * p.ldk + i0 + wm * 64 + p.diag_shift;
-                bulk_s2g(dst, tb + lane * TS, 64 * 8);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            if (rpmir) {
-                // column sums over this warp's 64 rows = row-sum partial of mirrored row j for the
-                // 64-column slot [i0 + wm*64, +64) of that row: slot index = 2*(i0/BM) + wm
-                const long slot = p.diag_shift / BN + 2 * (i0 / BM) + wm;
-                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);
-                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
-                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);
-                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
-                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16);
-                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
-                if (g == 0) {
-                    double* r = rpmir + slot * p.rows_pad + (jb - mir_row0) + nt * 8;
-                    *reinterpret_cast<double2*>(r) = make_double2(cs0, cs1);
-                }
+            *ptr = make_double2(v0, v1);
+            rsum += v0 + v1;
+            if (MIRROR) {
+                // element (row j0 + col, column i) of the symmetric matrix: lanes = consecutive i
+                __stcs(mir + (long)col * p.ldk, v0);
+                __stcs(mir + (long)(col + 1) * p.ldk, v1);
             }
         }
     }
-    {
-        // both staging buffers free again before the next tile touches them
-        if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-    }
-    if (p.rowpart) {
-#pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
-            double v = sacc[mt];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = v;
-        }
-    }
+    return rsum;
 }
 
 template <int KID>
-__global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* smem = reinterpret_cast<double*>(smem_raw);
-    double* rs = smem + (size_t)STAGES * STAGE_D;                  // [2 bufs][2 halves][BM]
-    uint64_t* full = reinterpret_cast<uint64_t*>(rs + 4 * BM);
-    uint64_t* empty = full + STAGES;
-    double* tstage = rs + 4 * BM + 16;                             // after the 128 bytes of mbarriers
+__global__ void __launch_bounds__(NTHREADS, 1)
+gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmK, const GramParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array itself (a round trip through
+    // an integer makes the compiler lose the address space and emit generic LD / ST)
+    unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* S = base;                                       // staging tile (1024-byte aligned)
+    double* coln = reinterpret_cast<double*>(base + OFF_COLN);     // pre-scaled column norms of the tile
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + OFF_BARS);
+    uint64_t* empty = full + NST;
+    uint64_t* acc_full = empty + NST;
+    uint64_t* acc_empty = acc_full + 1;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
     const int KT = p.kt;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        mbar_init(acc_full, 8);
+        mbar_init(acc_empty, 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    if (warp >= 4) {
-        // ---------------- producer warpgroup: hands its registers to the MMA warps ----------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp != 4) return;
+    if (warp >= 12) {
+        // ------------------------------ producer warpgroup ------------------------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp != 12 || lane != 0) return;
         int it = 0;
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
@@ -236,65 +196,107 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
             int peer;
             if (tile_role(p, (int)(i0 / BM), tx, peer) == 0) continue;      // produced by a mirror store
             for (int kt = 0; kt < KT; ++kt, ++it) {
-                const int s = it % STAGES;
-                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);    // passes at once on first use
-                double* As = smem + (size_t)s * STAGE_D;
-                double* Bs = As + BK * AS;
-                if (lane == 0) mbar_arrive_expect_tx(&full[s], BK * (BM + BN) * 8);
-                __syncwarp();
-                if (lane < BK)
-                    bulk_g2s(As + lane * AS, p.A + (long)(kt * BK + lane) * p.lda + i0, BM * 8, &full[s]);
-                else
-                    bulk_g2s(Bs + (lane - BK) * BS, p.B + (long)(kt * BK + lane - BK) * p.ldb + j0, BN * 8,
-                             &full[s]);
+                const int s = it % NST;
+                mbar_wait(&empty[s], ((it / NST) & 1) ^ 1);       // passes at once on first use
+                unsigned char* st = base + OFF_STAGES + s * STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+                tma_load_2d(st, &tmA, (int)i0, kt * BK, &full[s], L2_EVICT_LAST);
+                tma_load_2d(st + SLAB_BYTES, &tmB, (int)j0, kt * BK, &full[s], L2_EVICT_LAST);
             }
         }
         return;
     }
 
+    if (warp >= 8) {
+        // ------------------------------ epilogue warpgroup ------------------------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        const int e = tid - EPI_TID0;                              // tile row owned by this thread
+        int tcount = 0;
+        for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            long i0, j0; int tx;
+            tile_coords(p, tile, i0, j0, tx);
+            int peer;
+            const int role = tile_role(p, (int)(i0 / BM), tx, peer);
+            if (role == 0) continue;
+            const bool mirror = role == 2;
+            double ni = 0.0;
+            if (KID == 0) {
+                ni = -p.km.p0 * p.na[i0 + e];
+                coln[e] = -p.km.p0 * p.nb[j0 + e];
+            }
+            bar_sync_epilogue();                                   // column norms of this tile are in place
+            mbar_wait(acc_full, tcount & 1);                       // the MMA warps delivered the dot products
+            const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
+            const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
+                              (ig0 < j0 + BN && ig0 + BM > j0);
+            double rsum;
+            double* Kmir = nullptr; double* rpmir = nullptr; long mir_row0 = 0;
+            if (mirror) {
+                Kmir = (p.sym == 2) ? p.peerK[peer] : p.K;
+                rpmir = (p.sym == 2) ? p.peerRowpart[peer] : p.rowpart;
+                mir_row0 = (p.sym == 2) ? (long)peer * p.rows_pad : p.diag_shift;
+                double* mir = Kmir + (j0 - mir_row0) * p.ldk + (i0 + e + p.diag_shift);
+                rsum = edge ? gram_epilogue_row<KID, true, true>(p, S, coln, e, i0, j0, ni, mir)
+                            : gram_epilogue_row<KID, false, true>(p, S, coln, e, i0, j0, ni, mir);
+            } else {
+                rsum = edge ? gram_epilogue_row<KID, true, false>(p, S, coln, e, i0, j0, ni, nullptr)
+                            : gram_epilogue_row<KID, false, false>(p, S, coln, e, i0, j0, ni, nullptr);
+            }
+            if (p.rowpart) p.rowpart[(long)tx * p.rows_pad + i0 + e] = rsum;
+            fence_proxy_async();                                   // staging writes -> visible to the TMA store
+            bar_sync_epilogue();
+            if (e == 0) {
+                tma_store_3d(&tmK, S, 0, (int)i0, (int)(j0 / 16), L2_EVICT_FIRST);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (mirror && rpmir) {
+                // column sums of the mapped tile = row-sum partials of the mirrored rows, slot =
+                // tile-column index of this tile's rows in the owner's matrix; thread e sums column e
+                const int c = e >> 4, u = (e & 15) >> 1, h = (e & 1) * 8;
+                double cs = 0.0;
+#pragma unroll 8
+                for (int r = 0; r < BM; ++r) cs += *reinterpret_cast<const double*>(S + stage_off(r, c, u) + h);
+                const long slot = (i0 + p.diag_shift) / BN;
+                rpmir[slot * p.rows_pad + (j0 - mir_row0) + e] = cs;
+            }
+            if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            bar_sync_epilogue();                                   // store engine and all readers are done with S
+            if (e == 0) mbar_arrive(acc_empty);
+            ++tcount;
+        }
+        if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+
     // -------------------------------- MMA warps --------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int wm = warp >> 1, wn = warp & 1;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
     int it = 0, tcount = 0;
     for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         long i0, j0; int tx;
         tile_coords(p, tile, i0, j0, tx);
         int peer;
-        const int role = tile_role(p, (int)(i0 / BM), tx, peer);
-        if (role == 0) continue;
-        const bool mirror = role == 2;
-        ++tcount;
+        if (tile_role(p, (int)(i0 / BM), tx, peer) == 0) continue;
         double acc[8][4][2];
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-        // squared norms for the Gaussian map: requested now, consumed after the main loop
-        double ni[8], nbv[4][2];
-#pragma unroll
-        for (int mt = 0; mt < 8; ++mt) ni[mt] = (KID == 0) ? -p.km.p0 * p.na[i0 + wm * 64 + mt * 8 + g] : 0.0;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            nbv[nt][0] = nbv[nt][1] = 0.0;
-            if (KID == 0) {
-                const double2 v = *reinterpret_cast<const double2*>(p.nb + j0 + wn * 32 + nt * 8 + 2 * t);
-                nbv[nt][0] = -p.km.p0 * v.x; nbv[nt][1] = -p.km.p0 * v.y;   // pre-scaled by -gamma (gram_map)
-            }
-        }
 
         for (int kt = 0; kt < KT; ++kt, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(&full[s], (it / STAGES) & 1);
-            const double* As = smem + (size_t)s * STAGE_D + wm * 64 + g;
-            const double* Bs = smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g;
+            const int s = it % NST;
+            mbar_wait(&full[s], (it / NST) & 1);
+            const double* As = reinterpret_cast<const double*>(base + OFF_STAGES + s * STAGE_BYTES) + wm * 64 + g;
+            const double* Bs = reinterpret_cast<const double*>(base + OFF_STAGES + s * STAGE_BYTES + SLAB_BYTES) + wn * 32 + g;
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) {
                 double a[8], b[4];
                 const int kr = kk * 4 + t;
 #pragma unroll
-                for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * AS + mt * 8];
+                for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * PITCH + mt * 8];
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * BS + nt * 8];
+                for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * PITCH + nt * 8];
 #pragma unroll
                 for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
@@ -304,27 +306,21 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
             if (lane == 0) mbar_arrive(&empty[s]);               // this warp is done with stage s
         }
 
-        // ---- epilogue: map in registers, shuffle row sums, direct 16-byte stores ----
-        double* rsb = rs + (tcount & 1) * 2 * BM;
-        const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
-        const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
-                          (ig0 < j0 + BN && ig0 + BM > j0);
-        if (mirror) {
-            double* Kmir = (p.sym == 2) ? p.peerK[peer] : p.K;
-            double* rpmir = (p.sym == 2) ? p.peerRowpart[peer] : p.rowpart;
-            const long mir_row0 = (p.sym == 2) ? (long)peer * p.rows_pad : p.diag_shift;
-            if (edge) gram_epilogue_mirror<KID, true>(p, acc, ni, i0, j0, wm, wn, g, t, rsb, Kmir, rpmir, mir_row0, tstage + warp * 2 * TBUF_D);
-            else      gram_epilogue_mirror<KID, false>(p, acc, ni, i0, j0, wm, wn, g, t, rsb, Kmir, rpmir, mir_row0, tstage + warp * 2 * TBUF_D);
-        } else {
-            if (edge) gram_epilogue_plain<KID, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
-            else      gram_epilogue_plain<KID, false>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+        // hand the raw dot products to the epilogue warps and go on with the next tile
+        mbar_wait(acc_empty, (tcount & 1) ^ 1);                  // passes at once for the first tile
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+            const int r = wm * 64 + mt * 8 + g;                  // r & 7 == g
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int c = wn * 2 + (nt >> 1), u = (nt & 1) * 4 + t;
+                *reinterpret_cast<double2*>(S + stage_off(r, c, u)) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            }
         }
-        if (p.rowpart) {
-            bar_sync_compute();                  // both column halves of every row are in smem
-            p.rowpart[(long)tx * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_full);
+        ++tcount;
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // mirrored tiles have left the SM
 }
 
 // ---- naive cross-check variant: one thread per output element -------------------------------
@@ -349,7 +345,7 @@ __global__ void gram_naive_rowpart_kernel(const double* K, long ldk, double* row
     const long jt = blockIdx.y;
     if (i >= rows_pad) return;
     double s = 0.0;
-    for (int c = 0; c < 64; ++c) s += K[i * ldk + jt * 64 + c];
+    for (int c = 0; c < BN; ++c) s += K[i * ldk + jt * BN + c];
     rowpart[jt * rows_pad + i] = s;
 }
 
@@ -364,7 +360,23 @@ __global__ void rownorms_kernel(const double* P, long ld, long nobs, int d_pad, 
     norms[i] = s;
 }
 
+bool use_v3() {
+    static const bool v = []() { const char* e = getenv("FXB200_GRAM_V3"); return e && e[0] == '1'; }();
+    return v;
+}
+
+template <int KID>
+int launch_ws(fx_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmK,
+              const GramParams& p, unsigned grid) {
+    FX_SET_SMEM_ONCE(ctx, gram_ws_kernel<KID>, SMEM_BYTES);
+    gram_ws_kernel<KID><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmK, p);
+    return 0;
+}
+
 }  // namespace
+
+// Number of per-tile row-sum partials (slots of `rowpart`) the Gram kernel writes per row.
+int64_t fx_gram_rowpart_slots(int64_t ldk) { return use_v3() ? ldk / 64 : ldk / BN; }
 
 int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, int64_t d_pad,
                        double* norms) {
@@ -376,7 +388,8 @@ int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, i
 }
 
 int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
-    if (a.rows_pad % BM || a.ldk % BN || a.d_pad % BK || a.lda % 2 || a.ldb % 2) {
+    if (use_v3()) return fx_launch_gram_v3(ctx, a, variant);
+    if (a.rows_pad % BM || a.ldk % BN || a.d_pad % 16 || a.lda % 2 || a.ldb % 2) {
         fx_set_error("gram: bad padding rows_pad=%lld ldk=%lld d_pad=%lld", (long long)a.rows_pad,
                      (long long)a.ldk, (long long)a.d_pad);
         return FX_ERR_CUDA;
@@ -412,25 +425,46 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     }
     if (a.rows_pad == 0 || a.ldk == 0) return 0;
     if (variant == 0) {
-        if (!fx_attr_once(ctx, (const void*)gram_dmma_kernel<0>)) {
-            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            FX_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PFN_encodeTiled enc = get_encode();
+        if (!enc) {
+            fx_set_error("gram: cuTensorMapEncodeTiled is not available from this driver");
+            return FX_ERR_CUDA;
         }
-        long want = 2L * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+        CUtensorMap tmA, tmB, tmK;
+        auto operand_map = [&](CUtensorMap* tm, const double* ptr, int64_t nobs, int64_t ld) -> int {
+            // feature-major operand: dim0 = observations (contiguous), dim1 = features
+            cuuint64_t dims[2] = {(cuuint64_t)nobs, (cuuint64_t)a.d_pad};
+            cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+            cuuint32_t box[2] = {PITCH, BK};
+            cuuint32_t es[2] = {1, 1};
+            CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ptr, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { fx_set_error("gram: operand tensor map rejected (CUresult %d)", (int)r); return FX_ERR_CUDA; }
+            return 0;
+        };
+        FX_TRY(operand_map(&tmA, a.A, a.rows_pad, a.lda));
+        FX_TRY(operand_map(&tmB, a.B, a.ldk, a.ldb));
+        {
+            cuuint64_t dims[3] = {16, (cuuint64_t)a.rows_pad, (cuuint64_t)(a.ldk / 16)};
+            cuuint64_t strides[2] = {(cuuint64_t)a.ldk * 8, 128};
+            cuuint32_t box[3] = {16, BM, BN / 16};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUresult r = enc(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)a.K, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { fx_set_error("gram: tensor map for K rejected (CUresult %d)", (int)r); return FX_ERR_CUDA; }
+        }
+        const long want = ctx->sm_count > 0 ? ctx->sm_count : 148;
         const unsigned grid = (unsigned)(p.tiles_total < want ? p.tiles_total : want);
         switch (kernel_variant(p.km.id, p.km.ipow)) {
-            case 0: gram_dmma_kernel<0><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
-            case 1: gram_dmma_kernel<1><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
-            case 2: gram_dmma_kernel<2><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
-            case 3: gram_dmma_kernel<3><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
-            case 4: gram_dmma_kernel<4><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
-            case 5: gram_dmma_kernel<5><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
-            default: gram_dmma_kernel<6><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p); break;
+            case 0: FX_TRY(launch_ws<0>(ctx, tmA, tmB, tmK, p, grid)); break;
+            case 1: FX_TRY(launch_ws<1>(ctx, tmA, tmB, tmK, p, grid)); break;
+            case 2: FX_TRY(launch_ws<2>(ctx, tmA, tmB, tmK, p, grid)); break;
+            case 3: FX_TRY(launch_ws<3>(ctx, tmA, tmB, tmK, p, grid)); break;
+            case 4: FX_TRY(launch_ws<4>(ctx, tmA, tmB, tmK, p, grid)); break;
+            case 5: FX_TRY(launch_ws<5>(ctx, tmA, tmB, tmK, p, grid)); break;
+            default: FX_TRY(launch_ws<6>(ctx, tmA, tmB, tmK, p, grid)); break;
         }
         ctx->launches++;
     } else {
@@ -438,7 +472,7 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
         gram_naive_kernel<<<grid, 256, 0, ctx->stream>>>(p, (int)a.d_pad);
         ctx->launches++;
         if (a.rowpart) {
-            dim3 g2((unsigned)ceil_div(a.rows_pad, 256), (unsigned)(a.ldk / 64));
+            dim3 g2((unsigned)ceil_div(a.rows_pad, 256), (unsigned)(a.ldk / BN));
             gram_naive_rowpart_kernel<<<g2, 256, 0, ctx->stream>>>(a.K, a.ldk, a.rowpart, a.rows_pad);
             ctx->launches++;
         }

@@ -363,10 +363,9 @@ int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int l
     int nwarps = (half + per - 1) / per;
     if (nwarps < 2) nwarps = 2;
     const int threads = 32 * nwarps;
-    if (!fx_attr_once(ctx, (const void*)jacobi_kernel<true, true>)) {
-        FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_MAX_DYN_SMEM));
-        FX_CUDA(cudaFuncSetAttribute(jacobi_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_MAX_DYN_SMEM));
-    }
+    // largest dynamic request of each mode (the kernel also holds ~17 KB of static shared memory)
+    FX_SET_SMEM_ONCE(ctx, (jacobi_kernel<true, true>), 2 * J_SMEM_BOTH_MAX_M * (J_SMEM_BOTH_MAX_M | 1) * 8);
+    FX_SET_SMEM_ONCE(ctx, (jacobi_kernel<true, false>), J_SMEM_MAX_M * (J_SMEM_MAX_M | 1) * 8);
     if (mode == 2) jacobi_kernel<true, true><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40, need);
     else if (mode == 1) jacobi_kernel<true, false><<<1, threads, smem, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40, need);
     else jacobi_kernel<false, false><<<1, threads, 0, ctx->stream>>>(A, lda, m, Vwork, m, w, Vout, ldv, info, 40, need);
@@ -392,8 +391,7 @@ int fx_launch_chol_factors(fx_ctx* ctx, const double* G, int ldg, int b, double 
         return FX_ERR_CUDA;
     }
     const size_t smem = (2 * 64 * 65 + 64) * sizeof(double);
-    if (!fx_attr_once(ctx, (const void*)chol_factors_kernel))
-        FX_CUDA(cudaFuncSetAttribute(chol_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FX_SET_SMEM_ONCE(ctx, chol_factors_kernel, smem);
     chol_factors_kernel<<<1, 256, smem, ctx->stream>>>(G, ldg, b, thr, M, Cfac, need_svqb, ndef);
     ctx->launches++;
     FX_LAUNCH_CHECK();

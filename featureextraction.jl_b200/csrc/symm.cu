@@ -90,8 +90,8 @@ symm_dmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant_
                  const SymmParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment so that (address bits 7..9) == (row & 7) for the 128-byte swizzle
-    unsigned char* base = reinterpret_cast<unsigned char*>(
-        (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    // (pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST)
+    unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     constexpr int K_BYTES = RT * BKC * 8;                 // 65536
     constexpr int V_BYTES = NB * 8 * BKC * 8;             // NB * 4096
     constexpr int C_BYTES = CENTER ? 1024 : 0;            // 64 column means (512 B) + pad
@@ -275,8 +275,7 @@ int launch_nb(fx_ctx* ctx, const CUtensorMap& tmK, const CUtensorMap& tmV, SymmP
     if (ns > 4) ns = 4;
     p.nstage = ns;
     const int smem = ns * STAGE_BYTES + 1024 + 128;
-    if (!fx_attr_once(ctx, (const void*)symm_dmma_kernel<NB, CENTER>))
-        FX_CUDA(cudaFuncSetAttribute(symm_dmma_kernel<NB, CENTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FX_SET_SMEM_ONCE(ctx, (symm_dmma_kernel<NB, CENTER>), smem);
     const unsigned grid = (unsigned)((p.rows_pad / RT) * p.splits);
     symm_dmma_kernel<NB, CENTER><<<grid, CENTER ? 320 : 288, smem, ctx->stream>>>(tmK, tmV, p);
     ctx->launches++;

@@ -194,15 +194,19 @@ __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
         const double* Wt = Wsm + (size_t)ws * NBK * 8 * WS + g * WS + 2 * t;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
+            double2 wv[NBK];
 #pragma unroll
-            for (int nk = 0; nk < NBK; ++nk) {
-                const double2 wv = *reinterpret_cast<const double2*>(Wt + nk * 8 * WS + nt * 8);
+            for (int nk = 0; nk < NBK; ++nk) wv[nk] = *reinterpret_cast<const double2*>(Wt + nk * 8 * WS + nt * 8);
+            // the two MMAs that update the same accumulator are kept 2*NBK issues apart (a DMMA that
+            // waits for its predecessor's result stalls the warp for the pipe latency)
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    dmma(acc2[mt][nk][0], acc2[mt][nk][1], acc1[mt][nt][0], wv.x);
-                    dmma(acc2[mt][nk][0], acc2[mt][nk][1], acc1[mt][nt][1], wv.y);
-                }
-            }
+            for (int nk = 0; nk < NBK; ++nk)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) dmma(acc2[mt][nk][0], acc2[mt][nk][1], acc1[mt][nt][0], wv[nk].x);
+#pragma unroll
+            for (int nk = 0; nk < NBK; ++nk)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) dmma(acc2[mt][nk][0], acc2[mt][nk][1], acc1[mt][nt][1], wv[nk].y);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&wempty[ws]);
@@ -288,8 +292,7 @@ __global__ void transform_naive_kernel(const TrParams p, int d_pad, long m_pad) 
 template <int NBK, int KID>
 int launch_tr2(fx_ctx* ctx, const TrParams& p, long m_pad) {
     constexpr int SMEM = (TST * TSTAGE_D + 2 * NBK * 8 * WS + 2 * TN) * 8 + 128;
-    if (!fx_attr_once(ctx, (const void*)transform_kernel<NBK, KID>)) 
-        FX_CUDA(cudaFuncSetAttribute(transform_kernel<NBK, KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    FX_SET_SMEM_ONCE(ctx, (transform_kernel<NBK, KID>), SMEM);
     dim3 grid((unsigned)(m_pad / TQ), (unsigned)p.nsplit);
     transform_kernel<NBK, KID><<<grid, 288, SMEM, ctx->stream>>>(p);
     ctx->launches++;

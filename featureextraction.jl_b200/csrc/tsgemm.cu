@@ -262,8 +262,7 @@ int fx_launch_ts_nn(fx_ctx* ctx, const double* A, int ma, const double* M, int l
     }
     const int ma16 = (ma + 15) & ~15;
     const size_t smem = (size_t)32 * (ma16 + 2) * 8;
-    if (!fx_attr_once(ctx, (const void*)ts_nn_kernel))
-        FX_CUDA(cudaFuncSetAttribute(ts_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_MAX_DYN_SMEM));
+    FX_SET_SMEM_ONCE(ctx, ts_nn_kernel, FX_MAX_DYN_SMEM);
     dim3 grid((unsigned)(rows / 128), (unsigned)ceil_div(nc, 32));
     ts_nn_kernel<<<grid, 256, smem, ctx->stream>>>(p);
     ctx->launches++;
