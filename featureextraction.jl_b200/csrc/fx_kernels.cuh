@@ -30,7 +30,7 @@ struct GramArgs {
 int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, int64_t d_pad,
                        double* norms);
 int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant);
-// slots of GramArgs::rowpart per row: one partial row sum per 128-column output tile
+// slots of GramArgs::rowpart per row: one partial row sum per 64 columns
 int64_t fx_gram_rowpart_slots(int64_t ldk);
 
 // ---- center.cu -------------------------------------------------------------------------

@@ -2,17 +2,17 @@
 // per-tile row sums fused behind the contraction.  Replaces MLKernels.kernelmatrix as called at
 // /root/reference/src/kpca.jl:51 (symmetric) and kpca.jl:65 (cross).
 //
-// One persistent CTA per SM, warp-specialised (512 threads, setmaxnreg 200 / 88 / 24):
-//   producer (warp 12, one lane): per 8-feature step TWO tensor-map bulk copies (TMA, SASS UTMALDG),
+// One persistent CTA per SM, warp-specialised (640 threads, setmaxnreg 168 / 56 / 24):
+//   producer (warp 16, one lane): per 8-feature step TWO tensor-map bulk copies (TMA, SASS UTMALDG),
 //     boxes of {132 observations x 8 features} of the row and of the column operand -- the box is 4
 //     elements wider than the 128 it feeds, which makes the shared-memory row pitch 132 doubles and
-//     the LDS.64 fragment reads conflict free (t*132 + g distinct mod 16) -- into a 5-stage ring
+//     the LDS.64 fragment reads conflict free (t*132 + g distinct mod 16) -- into a 4-stage ring
 //     guarded by mbarrier full/empty pairs; it runs ahead across tile boundaries.
 //   8 MMA warps (2 x 4, 64 x 32 register tile each, DMMA.8x8x4 = mma.sync f64): main loop only.
 //     When a 128 x 128 tile is done they drop the RAW dot products into a 128 KB staging tile in
 //     shared memory (the layout a 128-byte-swizzled TMA store expects) and start the next tile at
 //     once -- the kernel map never stops the DMMA stream of an SM.
-//   4 epilogue warps (one thread per tile row): kernel map in place in the staging tile (branch-free
+//   8 epilogue warps (one thread per half tile row): kernel map in place in the staging tile (branch-free
 //     exp / templated powers / tanh), row sums, then ONE tensor-map bulk store (UTMASTG) of the
 //     tile to K.  In round 1 the map ran inside the MMA warps and cost 20-30 % of the kernel.
 //
@@ -35,7 +35,7 @@ int fx_launch_gram_v3(fx_ctx* ctx, const GramArgs& a, int variant);      // gram
 
 namespace {
 
-constexpr int BM = FX_GRAM_BM, BN = FX_GRAM_BN, BK = 8, NST = 5;
+constexpr int BM = FX_GRAM_BM, BN = FX_GRAM_BN, BK = 8, NST = 4;
 constexpr int PITCH = 132;                                   // doubles per staged operand row
 constexpr int SLAB_BYTES = BK * PITCH * 8;                   // 8448 (multiple of 128)
 constexpr int STAGE_BYTES = 2 * SLAB_BYTES;
@@ -44,8 +44,9 @@ constexpr int OFF_STAGES = ACC_BYTES;
 constexpr int OFF_COLN = OFF_STAGES + NST * STAGE_BYTES;
 constexpr int OFF_BARS = OFF_COLN + BN * 8;
 constexpr int SMEM_BYTES = OFF_BARS + 128 + 1024;            // + slack for the 1024-byte alignment
-constexpr int NTHREADS = 512;
-constexpr int EPI_THREADS = 128, EPI_TID0 = 256;
+constexpr int NTHREADS = 640;                                // 8 MMA + 8 epilogue + 4 producer-group warps
+constexpr int EPI_THREADS = 256, EPI_TID0 = 256;
+constexpr int HALF = BN / 2;                                 // columns per epilogue thread
 constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* 
         "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)), "l"(hint)
         : "memory");
 }
-__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Byte offset of the 16-byte unit that holds columns (2u', 2u'+1) of chunk `c` in row `r` of the
 // staging tile: [chunk of 16 columns][row][128 bytes], the eight 16-byte units of a row XOR-swizzled
@@ -113,45 +114,53 @@ __device__ __forceinline__ double gram_map(const KernelMap& km, double dot, doub
     return kernel_map_t<KID>(km, dot, ni, nj, same);
 }
 
-// Epilogue pass over one tile row (thread e owns row e of the staging tile): map in place, row sum,
-// and -- for MIRROR tiles -- the transposed stores into the owner's K.  EDGE tiles (ragged borders
-// or touching the diagonal) carry the validity masks and the same-point test.
+// Epilogue pass over half a tile row (thread e owns row e & 127, columns [64 h, 64 h + 64) with
+// h = e >> 7): map in place, row sum, and -- for MIRROR tiles -- the transposed stores into the
+// owner's K.  EDGE tiles (ragged borders or touching the diagonal) carry the validity masks and the
+// same-point test.  Two epilogue warps per scheduler: the FP64 operations of the map share one
+// datapath with the DMMAs of the MMA warps, and a single warp per scheduler gets too few issue
+// grants between the DMMAs (measured: the MMA warps then wait for the staging tile 20 % of the time).
 template <int KID, bool EDGE, bool MIRROR>
 __device__ __forceinline__ double gram_epilogue_row(const GramParams& p, unsigned char* S, const double* coln,
-                                                    int e, long i0, long j0, double ni, double* mir) {
-    const long i = i0 + e;
+                                                    int row, int h, long i0, long j0, double ni, double* mir) {
+    const long i = i0 + row;
     const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
     const bool iv = i < p.rows_valid;
     double rsum = 0.0;
 #pragma unroll 1
-    for (int c = 0; c < BN / 16; ++c) {
+    for (int cc = 0; cc < HALF / 16; ++cc) {
+        const int c = h * (HALF / 16) + cc;
+#pragma unroll 1
+        for (int uh = 0; uh < 8; uh += 4) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            double2* ptr = reinterpret_cast<double2*>(S + stage_off(e, c, u));
-            const double2 dv = *ptr;
-            const int col = c * 16 + u * 2;
-            double n0 = 0.0, n1 = 0.0;
-            if (KID == 0) {
-                const double2 nn = *reinterpret_cast<const double2*>(coln + col);     // broadcast read
-                n0 = nn.x; n1 = nn.y;
-            }
-            double v0, v1;
-            if (EDGE) {
-                const long j = j0 + col;
-                v0 = gram_map<KID>(p.km, dv.x, ni, n0, ig == j);
-                v1 = gram_map<KID>(p.km, dv.y, ni, n1, ig == j + 1);
-                v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
-                v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
-            } else {
-                v0 = gram_map<KID>(p.km, dv.x, ni, n0, false);
-                v1 = gram_map<KID>(p.km, dv.y, ni, n1, false);
-            }
-            *ptr = make_double2(v0, v1);
-            rsum += v0 + v1;
-            if (MIRROR) {
-                // element (row j0 + col, column i) of the symmetric matrix: lanes = consecutive i
-                __stcs(mir + (long)col * p.ldk, v0);
-                __stcs(mir + (long)(col + 1) * p.ldk, v1);
+            for (int uu = 0; uu < 4; ++uu) {
+                const int u = uh + uu;
+                double2* ptr = reinterpret_cast<double2*>(S + stage_off(row, c, u));
+                const double2 dv = *ptr;
+                const int col = c * 16 + u * 2;
+                double n0 = 0.0, n1 = 0.0;
+                if (KID == 0) {
+                    const double2 nn = *reinterpret_cast<const double2*>(coln + col);     // broadcast read
+                    n0 = nn.x; n1 = nn.y;
+                }
+                double v0, v1;
+                if (EDGE) {
+                    const long j = j0 + col;
+                    v0 = gram_map<KID>(p.km, dv.x, ni, n0, ig == j);
+                    v1 = gram_map<KID>(p.km, dv.y, ni, n1, ig == j + 1);
+                    v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
+                    v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
+                } else {
+                    v0 = gram_map<KID>(p.km, dv.x, ni, n0, false);
+                    v1 = gram_map<KID>(p.km, dv.y, ni, n1, false);
+                }
+                *ptr = make_double2(v0, v1);
+                rsum += v0 + v1;
+                if (MIRROR) {
+                    // element (row j0 + col, column i) of the symmetric matrix: lanes = consecutive i
+                    __stcs(mir + (long)col * p.ldk, v0);
+                    __stcs(mir + (long)(col + 1) * p.ldk, v1);
+                }
             }
         }
     }
@@ -185,10 +194,10 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncthreads();
 
-    if (warp >= 12) {
+    if (warp >= 16) {
         // ------------------------------ producer warpgroup ------------------------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (warp != 12 || lane != 0) return;
+        if (warp != 16 || lane != 0) return;
         int it = 0;
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
@@ -209,8 +218,9 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp >= 8) {
         // ------------------------------ epilogue warpgroup ------------------------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-        const int e = tid - EPI_TID0;                              // tile row owned by this thread
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int e = tid - EPI_TID0;
+        const int row = e & (BM - 1), h = e >> 7;                  // tile row and column half of this thread
         int tcount = 0;
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
@@ -221,8 +231,8 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool mirror = role == 2;
             double ni = 0.0;
             if (KID == 0) {
-                ni = -p.km.p0 * p.na[i0 + e];
-                coln[e] = -p.km.p0 * p.nb[j0 + e];
+                ni = -p.km.p0 * p.na[i0 + row];
+                if (h == 0) coln[row] = -p.km.p0 * p.nb[j0 + row];
             }
             bar_sync_epilogue();                                   // column norms of this tile are in place
             mbar_wait(acc_full, tcount & 1);                       // the MMA warps delivered the dot products
@@ -235,14 +245,15 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 Kmir = (p.sym == 2) ? p.peerK[peer] : p.K;
                 rpmir = (p.sym == 2) ? p.peerRowpart[peer] : p.rowpart;
                 mir_row0 = (p.sym == 2) ? (long)peer * p.rows_pad : p.diag_shift;
-                double* mir = Kmir + (j0 - mir_row0) * p.ldk + (i0 + e + p.diag_shift);
-                rsum = edge ? gram_epilogue_row<KID, true, true>(p, S, coln, e, i0, j0, ni, mir)
-                            : gram_epilogue_row<KID, false, true>(p, S, coln, e, i0, j0, ni, mir);
+                double* mir = Kmir + (j0 - mir_row0) * p.ldk + (i0 + row + p.diag_shift);
+                rsum = edge ? gram_epilogue_row<KID, true, true>(p, S, coln, row, h, i0, j0, ni, mir)
+                            : gram_epilogue_row<KID, false, true>(p, S, coln, row, h, i0, j0, ni, mir);
             } else {
-                rsum = edge ? gram_epilogue_row<KID, true, false>(p, S, coln, e, i0, j0, ni, nullptr)
-                            : gram_epilogue_row<KID, false, false>(p, S, coln, e, i0, j0, ni, nullptr);
+                rsum = edge ? gram_epilogue_row<KID, true, false>(p, S, coln, row, h, i0, j0, ni, nullptr)
+                            : gram_epilogue_row<KID, false, false>(p, S, coln, row, h, i0, j0, ni, nullptr);
             }
-            if (p.rowpart) p.rowpart[(long)tx * p.rows_pad + i0 + e] = rsum;
+            // row-sum partials: one slot per 64 columns (two per tile)
+            if (p.rowpart) p.rowpart[(long)(2 * tx + h) * p.rows_pad + i0 + row] = rsum;
             fence_proxy_async();                                   // staging writes -> visible to the TMA store
             bar_sync_epilogue();
             if (e == 0) {
@@ -250,14 +261,16 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             if (mirror && rpmir) {
-                // column sums of the mapped tile = row-sum partials of the mirrored rows, slot =
-                // tile-column index of this tile's rows in the owner's matrix; thread e sums column e
-                const int c = e >> 4, u = (e & 15) >> 1, h = (e & 1) * 8;
+                // column sums of the mapped tile = row-sum partials of the mirrored rows; thread e sums
+                // column `row` over the tile rows [64 h, 64 h + 64), which are columns
+                // [i0 + 64 h, +64) of the owner's matrix: slot = that 64-column block
+                const int c = row >> 4, u = (row & 15) >> 1, hb = (row & 1) * 8;
                 double cs = 0.0;
 #pragma unroll 8
-                for (int r = 0; r < BM; ++r) cs += *reinterpret_cast<const double*>(S + stage_off(r, c, u) + h);
-                const long slot = (i0 + p.diag_shift) / BN;
-                rpmir[slot * p.rows_pad + (j0 - mir_row0) + e] = cs;
+                for (int r = h * HALF; r < h * HALF + HALF; ++r)
+                    cs += *reinterpret_cast<const double*>(S + stage_off(r, c, u) + hb);
+                const long slot = (i0 + p.diag_shift) / HALF + h;
+                rpmir[slot * p.rows_pad + (j0 - mir_row0) + row] = cs;
             }
             if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             bar_sync_epilogue();                                   // store engine and all readers are done with S
@@ -269,7 +282,7 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     // -------------------------------- MMA warps --------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp >> 2, wn = warp & 3;
     int it = 0, tcount = 0;
@@ -345,7 +358,7 @@ __global__ void gram_naive_rowpart_kernel(const double* K, long ldk, double* row
     const long jt = blockIdx.y;
     if (i >= rows_pad) return;
     double s = 0.0;
-    for (int c = 0; c < BN; ++c) s += K[i * ldk + jt * BN + c];
+    for (int c = 0; c < 64; ++c) s += K[i * ldk + jt * 64 + c];
     rowpart[jt * rows_pad + i] = s;
 }
 
@@ -376,7 +389,7 @@ int launch_ws(fx_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const
 }  // namespace
 
 // Number of per-tile row-sum partials (slots of `rowpart`) the Gram kernel writes per row.
-int64_t fx_gram_rowpart_slots(int64_t ldk) { return use_v3() ? ldk / 64 : ldk / BN; }
+int64_t fx_gram_rowpart_slots(int64_t ldk) { return ldk / 64; }
 
 int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, int64_t d_pad,
                        double* norms) {
@@ -472,7 +485,7 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
         gram_naive_kernel<<<grid, 256, 0, ctx->stream>>>(p, (int)a.d_pad);
         ctx->launches++;
         if (a.rowpart) {
-            dim3 g2((unsigned)ceil_div(a.rows_pad, 256), (unsigned)(a.ldk / BN));
+            dim3 g2((unsigned)ceil_div(a.rows_pad, 256), (unsigned)(a.ldk / 64));
             gram_naive_rowpart_kernel<<<g2, 256, 0, ctx->stream>>>(a.K, a.ldk, a.rowpart, a.rows_pad);
             ctx->launches++;
         }
