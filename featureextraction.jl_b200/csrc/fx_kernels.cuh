@@ -156,6 +156,11 @@ void fx_resolve_opts(const fx_solver_opts* in, int k, fx_solver_opts* out);
 int fx_launch_vec_axpy(fx_ctx* ctx, int64_t n, double a, const double* x, double* y);
 int fx_launch_copy2d(fx_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd, int rows,
                      int cols);
+// dst[:rows, :cols] += src[:rows, :cols]
+int fx_launch_copy2d_add(fx_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd, int rows,
+                         int cols);
+// G (b x b, ld b) = Hs[mq:mq+b, :] - Hs[:mq, :]' Hs[:mq, :]   (Hs is (mq + b) x b with leading dimension ldh)
+int fx_launch_gram_downdate(fx_ctx* ctx, const double* Hs, int ldh, int mq, int b, double* G);
 size_t fx_transform_scratch(fx_ctx* ctx, int64_t m_pad, int64_t n_ld, int kc, int* nsplit_out);
 int fx_launch_transform_ex(fx_ctx* ctx, const TransformArgs& a, int variant, double* scratch, int nsplit);
 int fx_launch_fill(fx_ctx* ctx, double* p, int64_t n, double v);

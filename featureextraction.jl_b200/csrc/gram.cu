@@ -2,19 +2,26 @@
 // per-tile row sums fused behind the contraction.  Replaces MLKernels.kernelmatrix as called at
 // /root/reference/src/kpca.jl:51 (symmetric) and kpca.jl:65 (cross).
 //
-// One persistent CTA per SM, warp-specialised (640 threads, setmaxnreg 168 / 56 / 24):
-//   producer (warp 16, one lane): per 8-feature step TWO tensor-map bulk copies (TMA, SASS UTMALDG),
+// One persistent CTA per SM, warp-specialised (512 threads, setmaxnreg 200 / 88 / 24):
+//   producer (warp 12, one lane): per 8-feature step TWO tensor-map bulk copies (TMA, SASS UTMALDG),
 //     boxes of {132 observations x 8 features} of the row and of the column operand -- the box is 4
 //     elements wider than the 128 it feeds, which makes the shared-memory row pitch 132 doubles and
 //     the LDS.64 fragment reads conflict free (t*132 + g distinct mod 16) -- into a 4-stage ring
 //     guarded by mbarrier full/empty pairs; it runs ahead across tile boundaries.
-//   8 MMA warps (2 x 4, 64 x 32 register tile each, DMMA.8x8x4 = mma.sync f64): main loop only.
-//     When a 128 x 128 tile is done they drop the RAW dot products into a 128 KB staging tile in
-//     shared memory (the layout a 128-byte-swizzled TMA store expects) and start the next tile at
-//     once -- the kernel map never stops the DMMA stream of an SM.
-//   8 epilogue warps (one thread per half tile row): kernel map in place in the staging tile (branch-free
-//     exp / templated powers / tanh), row sums, then ONE tensor-map bulk store (UTMASTG) of the
-//     tile to K.  In round 1 the map ran inside the MMA warps and cost 20-30 % of the kernel.
+//   8 MMA warps (2 x 4, 64 x 32 register tile each, DMMA.8x8x4 = mma.sync f64).  When a 128 x 128
+//     tile is done they drop the RAW dot products into a 128 KB staging tile in shared memory (the
+//     layout a 128-byte-swizzled TMA store expects) and start the next tile at once.  The kernel map
+//     of tile T (branch-free exp / templated powers / tanh, in place in the staging tile) is
+//     SOFTWARE-PIPELINED INTO THE MAIN LOOP OF TILE T+1: each k-step's 64 DMMAs share a basic block
+//     with the map of a few staged elements, so the map's FP64 operations fill the issue gaps of
+//     the DMMA stream instead of stopping it.  (DMMA and DFMA share one FP64 datapath.  Measured
+//     this round: a map that runs as a burst after each tile -- round 1, inside the MMA warps --
+//     leaves the datapath idle while both warps of a scheduler are in their bursts, 77-80 %; a map
+//     in separate epilogue warps is starved by the DMMA stream, the MMA warps end up waiting for
+//     the staging tile, 73-76 %.)
+//   4 store warps: when the MMA warps have mapped a tile, ONE tensor-map bulk store (UTMASTG) sends
+//     it to K; mirrored tiles are also written transposed, and the per-tile row / column sums that
+//     feed the centring are formed here.
 //
 // Symmetry.  K is symmetric when A is a row block of B.  sym = 1 (one rank, or no peer access):
 // inside this rank's square diagonal block only the tiles on / right of the diagonal are computed
@@ -41,12 +48,13 @@ constexpr int SLAB_BYTES = BK * PITCH * 8;                   // 8448 (multiple o
 constexpr int STAGE_BYTES = 2 * SLAB_BYTES;
 constexpr int ACC_BYTES = BM * BN * 8;                       // 131072: the staging tile
 constexpr int OFF_STAGES = ACC_BYTES;
-constexpr int OFF_COLN = OFF_STAGES + NST * STAGE_BYTES;
-constexpr int OFF_BARS = OFF_COLN + BN * 8;
+constexpr int OFF_COLW = OFF_STAGES + NST * STAGE_BYTES;     // [8 warps][32] pre-scaled column norms of the staged tile
+constexpr int OFF_RSUM = OFF_COLW + 8 * 32 * 8;              // [8 warps][64] row sums of each warp's 64 x 32 block
+constexpr int OFF_BARS = OFF_RSUM + 8 * 64 * 8;
 constexpr int SMEM_BYTES = OFF_BARS + 128 + 1024;            // + slack for the 1024-byte alignment
-constexpr int NTHREADS = 640;                                // 8 MMA + 8 epilogue + 4 producer-group warps
-constexpr int EPI_THREADS = 256, EPI_TID0 = 256;
-constexpr int HALF = BN / 2;                                 // columns per epilogue thread
+constexpr int NTHREADS = 512;                                // 8 MMA + 4 store + 4 producer-group warps
+constexpr int ST_THREADS = 128, ST_TID0 = 256;
+constexpr int UNITS = 32;                                    // 16-byte units (2 elements) per lane per tile
 constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 
@@ -100,7 +108,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* 
         "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)), "l"(hint)
         : "memory");
 }
-__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_store() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Byte offset of the 16-byte unit that holds columns (2u', 2u'+1) of chunk `c` in row `r` of the
 // staging tile: [chunk of 16 columns][row][128 bytes], the eight 16-byte units of a row XOR-swizzled
@@ -114,60 +122,68 @@ __device__ __forceinline__ double gram_map(const KernelMap& km, double dot, doub
     return kernel_map_t<KID>(km, dot, ni, nj, same);
 }
 
-// Epilogue pass over half a tile row (thread e owns row e & 127, columns [64 h, 64 h + 64) with
-// h = e >> 7): map in place, row sum, and -- for MIRROR tiles -- the transposed stores into the
-// owner's K.  EDGE tiles (ragged borders or touching the diagonal) carry the validity masks and the
-// same-point test.  Two epilogue warps per scheduler: the FP64 operations of the map share one
-// datapath with the DMMAs of the MMA warps, and a single warp per scheduler gets too few issue
-// grants between the DMMAs (measured: the MMA warps then wait for the staging tile 20 % of the time).
-template <int KID, bool EDGE, bool MIRROR>
-__device__ __forceinline__ double gram_epilogue_row(const GramParams& p, unsigned char* S, const double* coln,
-                                                    int row, int h, long i0, long j0, double ni, double* mir) {
-    const long i = i0 + row;
-    const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
-    const bool iv = i < p.rows_valid;
-    double rsum = 0.0;
-#pragma unroll 1
-    for (int cc = 0; cc < HALF / 16; ++cc) {
-        const int c = h * (HALF / 16) + cc;
-#pragma unroll 1
-        for (int uh = 0; uh < 8; uh += 4) {
-#pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-                const int u = uh + uu;
-                double2* ptr = reinterpret_cast<double2*>(S + stage_off(row, c, u));
-                const double2 dv = *ptr;
-                const int col = c * 16 + u * 2;
-                double n0 = 0.0, n1 = 0.0;
-                if (KID == 0) {
-                    const double2 nn = *reinterpret_cast<const double2*>(coln + col);     // broadcast read
-                    n0 = nn.x; n1 = nn.y;
-                }
-                double v0, v1;
-                if (EDGE) {
-                    const long j = j0 + col;
-                    v0 = gram_map<KID>(p.km, dv.x, ni, n0, ig == j);
-                    v1 = gram_map<KID>(p.km, dv.y, ni, n1, ig == j + 1);
-                    v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
-                    v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
-                } else {
-                    v0 = gram_map<KID>(p.km, dv.x, ni, n0, false);
-                    v1 = gram_map<KID>(p.km, dv.y, ni, n1, false);
-                }
-                *ptr = make_double2(v0, v1);
-                rsum += v0 + v1;
-                if (MIRROR) {
-                    // element (row j0 + col, column i) of the symmetric matrix: lanes = consecutive i
-                    __stcs(mir + (long)col * p.ldk, v0);
-                    __stcs(mir + (long)(col + 1) * p.ldk, v1);
-                }
-            }
-        }
-    }
-    return rsum;
-}
+// Geometry of the in-place map: MMA warp (wm, wn) maps the 64 x 32 block it produced.  Lane L owns
+// rows wm*64 + L and wm*64 + L + 32 and walks the 16 units (2 chunks x 8) of each: unit q = 0..31 is
+// row L + 32 (q >> 4), chunk wn*2 + ((q >> 3) & 1), unit q & 7.  Lanes = consecutive rows, so the
+// swizzle makes every quarter-warp hit 8 distinct 16-byte units: conflict free.
+struct PrevTile {
+    long i0, j0;            // coordinates of the tile that sits (raw) in the staging tile
+    int q;                  // next unit to map (UNITS = done)
+    bool valid, edge;
+    double ni0, ni1;        // pre-scaled norms of this lane's two rows (Gaussian)
+    double rs, rs0;         // running row sum of the mapped values (this warp's 32 columns); rs0 = first row's
+                            // (scalars, no arrays: a run-time index would put the struct in local memory)
+};
 
 template <int KID>
+__device__ __forceinline__ void map_unit(const GramParams& p, unsigned char* S, const double* colw, int wm, int wn,
+                                         int lane, PrevTile& pv, int q) {
+    const int rsel = q >> 4, c = wn * 2 + ((q >> 3) & 1), u = q & 7;
+    double2* ptr = reinterpret_cast<double2*>(S + stage_off(wm * 64 + lane + 32 * rsel, c, u));
+    const double2 dv = *ptr;
+    double n0 = 0.0, n1 = 0.0;
+    if (KID == 0) {
+        const double2 nn = *reinterpret_cast<const double2*>(colw + (q & 15) * 2);         // broadcast read
+        n0 = nn.x; n1 = nn.y;
+    }
+    const double ni = rsel ? pv.ni1 : pv.ni0;
+    const double v0 = gram_map<KID>(p.km, dv.x, ni, n0, false);
+    const double v1 = gram_map<KID>(p.km, dv.y, ni, n1, false);
+    *ptr = make_double2(v0, v1);
+    if (q == 16) { pv.rs0 = pv.rs; pv.rs = 0.0; }              // second row starts
+    pv.rs += v0 + v1;
+}
+
+// EDGE tiles (ragged borders or touching the diagonal): validity masks and the same-point test;
+// mapped in one go before the main loop of the next tile (they are O(n / 128) of O((n / 128)^2) tiles).
+template <int KID>
+__device__ __forceinline__ void map_edge_tile(const GramParams& p, unsigned char* S, const double* colw, int wm, int wn,
+                                           int lane, PrevTile& pv) {
+    for (int q = pv.q; q < UNITS; ++q) {
+        const int rsel = q >> 4, c = wn * 2 + ((q >> 3) & 1), u = q & 7;
+        const int row = wm * 64 + lane + 32 * rsel;
+        double2* ptr = reinterpret_cast<double2*>(S + stage_off(row, c, u));
+        const double2 dv = *ptr;
+        double n0 = 0.0, n1 = 0.0;
+        if (KID == 0) { n0 = colw[(q & 15) * 2]; n1 = colw[(q & 15) * 2 + 1]; }
+        const long i = pv.i0 + row, j = pv.j0 + c * 16 + u * 2;
+        const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+        const bool iv = i < p.rows_valid;
+        const double ni = rsel ? pv.ni1 : pv.ni0;
+        double v0 = gram_map<KID>(p.km, dv.x, ni, n0, ig == j);
+        double v1 = gram_map<KID>(p.km, dv.y, ni, n1, ig == j + 1);
+        v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
+        v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
+        *ptr = make_double2(v0, v1);
+        if (q == 16) { pv.rs0 = pv.rs; pv.rs = 0.0; }
+        pv.rs += v0 + v1;
+    }
+    pv.q = UNITS;
+}
+
+// UPS = staged units mapped per k-step while a previous tile is pending (chosen by the launcher so
+// that the map is finished after about half of the k-steps: 32 / UPS <= kt / 2 where possible).
+template <int KID, int UPS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmK, const GramParams p) {
@@ -176,11 +192,10 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // an integer makes the compiler lose the address space and emit generic LD / ST)
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* S = base;                                       // staging tile (1024-byte aligned)
-    double* coln = reinterpret_cast<double*>(base + OFF_COLN);     // pre-scaled column norms of the tile
     uint64_t* full = reinterpret_cast<uint64_t*>(base + OFF_BARS);
     uint64_t* empty = full + NST;
-    uint64_t* acc_full = empty + NST;
-    uint64_t* acc_empty = acc_full + 1;
+    uint64_t* mapped = empty + NST;                                // staging tile holds K values (8 MMA warps arrive)
+    uint64_t* acc_empty = mapped + 1;                              // staging tile has been stored (store warps arrive)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KT = p.kt;
@@ -188,16 +203,16 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
-        mbar_init(acc_full, 8);
+        mbar_init(mapped, 8);
         mbar_init(acc_empty, 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    if (warp >= 16) {
+    if (warp >= 12) {
         // ------------------------------ producer warpgroup ------------------------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (warp != 16 || lane != 0) return;
+        if (warp != 12 || lane != 0) return;
         int it = 0;
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
@@ -205,7 +220,7 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int peer;
             if (tile_role(p, (int)(i0 / BM), tx, peer) == 0) continue;      // produced by a mirror store
             for (int kt = 0; kt < KT; ++kt, ++it) {
-                const int s = it % NST;
+                const int s = it & (NST - 1);
                 mbar_wait(&empty[s], ((it / NST) & 1) ^ 1);       // passes at once on first use
                 unsigned char* st = base + OFF_STAGES + s * STAGE_BYTES;
                 mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
@@ -217,10 +232,10 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     if (warp >= 8) {
-        // ------------------------------ epilogue warpgroup ------------------------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        const int e = tid - EPI_TID0;
-        const int row = e & (BM - 1), h = e >> 7;                  // tile row and column half of this thread
+        // ------------------------------ store warpgroup ------------------------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        const int e = tid - ST_TID0;                               // tile row (pass 1) / tile column (pass 2)
+        const double* rsum_w = reinterpret_cast<const double*>(base + OFF_RSUM);
         int tcount = 0;
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
@@ -228,52 +243,53 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int peer;
             const int role = tile_role(p, (int)(i0 / BM), tx, peer);
             if (role == 0) continue;
-            const bool mirror = role == 2;
-            double ni = 0.0;
-            if (KID == 0) {
-                ni = -p.km.p0 * p.na[i0 + row];
-                if (h == 0) coln[row] = -p.km.p0 * p.nb[j0 + row];
-            }
-            bar_sync_epilogue();                                   // column norms of this tile are in place
-            mbar_wait(acc_full, tcount & 1);                       // the MMA warps delivered the dot products
-            const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
-            const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
-                              (ig0 < j0 + BN && ig0 + BM > j0);
-            double rsum;
-            double* Kmir = nullptr; double* rpmir = nullptr; long mir_row0 = 0;
-            if (mirror) {
-                Kmir = (p.sym == 2) ? p.peerK[peer] : p.K;
-                rpmir = (p.sym == 2) ? p.peerRowpart[peer] : p.rowpart;
-                mir_row0 = (p.sym == 2) ? (long)peer * p.rows_pad : p.diag_shift;
-                double* mir = Kmir + (j0 - mir_row0) * p.ldk + (i0 + row + p.diag_shift);
-                rsum = edge ? gram_epilogue_row<KID, true, true>(p, S, coln, row, h, i0, j0, ni, mir)
-                            : gram_epilogue_row<KID, false, true>(p, S, coln, row, h, i0, j0, ni, mir);
-            } else {
-                rsum = edge ? gram_epilogue_row<KID, true, false>(p, S, coln, row, h, i0, j0, ni, nullptr)
-                            : gram_epilogue_row<KID, false, false>(p, S, coln, row, h, i0, j0, ni, nullptr);
-            }
-            // row-sum partials: one slot per 64 columns (two per tile)
-            if (p.rowpart) p.rowpart[(long)(2 * tx + h) * p.rows_pad + i0 + row] = rsum;
-            fence_proxy_async();                                   // staging writes -> visible to the TMA store
-            bar_sync_epilogue();
+            mbar_wait(mapped, tcount & 1);                         // the MMA warps finished the map of this tile
             if (e == 0) {
                 tma_store_3d(&tmK, S, 0, (int)i0, (int)(j0 / 16), L2_EVICT_FIRST);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            if (mirror && rpmir) {
-                // column sums of the mapped tile = row-sum partials of the mirrored rows; thread e sums
-                // column `row` over the tile rows [64 h, 64 h + 64), which are columns
-                // [i0 + 64 h, +64) of the owner's matrix: slot = that 64-column block
-                const int c = row >> 4, u = (row & 15) >> 1, hb = (row & 1) * 8;
-                double cs = 0.0;
+            if (p.rowpart) {
+                // row-sum partials, one slot per 64 columns: the four column blocks of the MMA warps, pairwise
+                const int wm = e >> 6, r = e & 63;
+                const double* rw = rsum_w + (wm * 4) * 64 + r;
+                p.rowpart[(long)(2 * tx) * p.rows_pad + i0 + e] = rw[0] + rw[64];
+                p.rowpart[(long)(2 * tx + 1) * p.rows_pad + i0 + e] = rw[128] + rw[192];
+            }
+            if (role == 2) {
+                double* Kmir = (p.sym == 2) ? p.peerK[peer] : p.K;
+                double* rpmir = (p.sym == 2) ? p.peerRowpart[peer] : p.rowpart;
+                const long mir_row0 = (p.sym == 2) ? (long)peer * p.rows_pad : p.diag_shift;
+                // transposed tile: thread e walks row e of the staging tile and writes column
+                // (i0 + e) of the owner's rows j0 - mir_row0 + ..: lanes = consecutive columns, so a
+                // warp's store covers 256 contiguous bytes of one mirrored row
+                double* mir = Kmir + (j0 - mir_row0) * p.ldk + (i0 + e + p.diag_shift);
+#pragma unroll 1
+                for (int c = 0; c < BN / 16; ++c) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const double2 v = *reinterpret_cast<const double2*>(S + stage_off(e, c, u));
+                        const int col = c * 16 + u * 2;
+                        __stcs(mir + (long)col * p.ldk, v.x);
+                        __stcs(mir + (long)(col + 1) * p.ldk, v.y);
+                    }
+                }
+                if (rpmir) {
+                    // column sums = row-sum partials of the mirrored rows; thread e sums column e over
+                    // the tile rows [0, 64) and [64, 128): columns [i0, +64), [i0 + 64, +64) of the owner
+                    const int c = e >> 4, u = (e & 15) >> 1, hb = (e & 1) * 8;
+                    double cs0 = 0.0, cs1 = 0.0;
 #pragma unroll 8
-                for (int r = h * HALF; r < h * HALF + HALF; ++r)
-                    cs += *reinterpret_cast<const double*>(S + stage_off(r, c, u) + hb);
-                const long slot = (i0 + p.diag_shift) / HALF + h;
-                rpmir[slot * p.rows_pad + (j0 - mir_row0) + row] = cs;
+                    for (int r = 0; r < 64; ++r) {
+                        cs0 += *reinterpret_cast<const double*>(S + stage_off(r, c, u) + hb);
+                        cs1 += *reinterpret_cast<const double*>(S + stage_off(r + 64, c, u) + hb);
+                    }
+                    const long slot = (i0 + p.diag_shift) / 64;
+                    rpmir[slot * p.rows_pad + (j0 - mir_row0) + e] = cs0;
+                    rpmir[(slot + 1) * p.rows_pad + (j0 - mir_row0) + e] = cs1;
+                }
             }
             if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            bar_sync_epilogue();                                   // store engine and all readers are done with S
+            bar_sync_store();                                      // store engine and all readers are done with S
             if (e == 0) mbar_arrive(acc_empty);
             ++tcount;
         }
@@ -282,44 +298,90 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     // -------------------------------- MMA warps --------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp >> 2, wn = warp & 3;
+    double* colw = reinterpret_cast<double*>(base + OFF_COLW) + warp * 32;
+    double* rsum_w = reinterpret_cast<double*>(base + OFF_RSUM) + warp * 64;
+    PrevTile pv;
+    pv.valid = false; pv.edge = false; pv.q = UNITS; pv.i0 = pv.j0 = 0;
+    pv.ni0 = pv.ni1 = pv.rs = pv.rs0 = 0.0;
     int it = 0, tcount = 0;
+
+    // signals that the staged tile is mapped: row sums out, staging writes ordered before the TMA store
+#define FX_GRAM_FINISH_PREV()                                                                                    \
+    {                                                                                                            \
+        rsum_w[lane] = pv.rs0;                                                                                   \
+        rsum_w[lane + 32] = pv.rs;                                                                               \
+        fence_proxy_async();                                                                                     \
+        __syncwarp();                                                                                            \
+        if (lane == 0) mbar_arrive(mapped);                                                                      \
+        pv.valid = false;                                                                                        \
+    }
+
     for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         long i0, j0; int tx;
         tile_coords(p, tile, i0, j0, tx);
         int peer;
         if (tile_role(p, (int)(i0 / BM), tx, peer) == 0) continue;
+        if (pv.valid && pv.edge) map_edge_tile<KID>(p, S, colw, wm, wn, lane, pv);   // before the accumulators are live
         double acc[8][4][2];
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-        for (int kt = 0; kt < KT; ++kt, ++it) {
-            const int s = it % NST;
-            mbar_wait(&full[s], (it / NST) & 1);
-            const double* As = reinterpret_cast<const double*>(base + OFF_STAGES + s * STAGE_BYTES) + wm * 64 + g;
-            const double* Bs = reinterpret_cast<const double*>(base + OFF_STAGES + s * STAGE_BYTES + SLAB_BYTES) + wn * 32 + g;
-#pragma unroll
-            for (int kk = 0; kk < BK / 4; ++kk) {
-                double a[8], b[4];
-                const int kr = kk * 4 + t;
-#pragma unroll
-                for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * PITCH + mt * 8];
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * PITCH + nt * 8];
-#pragma unroll
-                for (int mt = 0; mt < 8; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);               // this warp is done with stage s
+        // one k-step: 64 DMMAs on stage (it mod NST)
+#define FX_GRAM_KSTEP()                                                                                          \
+        {                                                                                                        \
+            const int s = it & (NST - 1);                                                                        \
+            mbar_wait(&full[s], (it / NST) & 1);                                                                 \
+            const double* As = reinterpret_cast<const double*>(base + OFF_STAGES + s * STAGE_BYTES) + wm * 64 + g; \
+            const double* Bs = reinterpret_cast<const double*>(base + OFF_STAGES + s * STAGE_BYTES + SLAB_BYTES) + wn * 32 + g; \
+            _Pragma("unroll")                                                                                    \
+            for (int kk = 0; kk < BK / 4; ++kk) {                                                                \
+                double a[8], b[4];                                                                               \
+                const int kr = kk * 4 + t;                                                                       \
+                _Pragma("unroll")                                                                                \
+                for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * PITCH + mt * 8];                                  \
+                _Pragma("unroll")                                                                                \
+                for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * PITCH + nt * 8];                                  \
+                _Pragma("unroll")                                                                                \
+                for (int mt = 0; mt < 8; ++mt)                                                                   \
+                    _Pragma("unroll")                                                                            \
+                    for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);           \
+            }                                                                                                    \
+        }
+#define FX_GRAM_KSTEP_END()                                                                                      \
+        {                                                                                                        \
+            __syncwarp();                                                                                        \
+            if (lane == 0) mbar_arrive(&empty[(it - 1) & (NST - 1)]);                                            \
         }
 
-        // hand the raw dot products to the epilogue warps and go on with the next tile
+        int kt = 0;
+        if (pv.valid) {
+            // phase 1: k-steps that also map UPS staged units of the previous tile (same basic block
+            // as the DMMAs: the scheduler interleaves the map's instructions with them)
+            for (; kt < KT && pv.q < UNITS; ++kt) {
+                FX_GRAM_KSTEP();
+#pragma unroll
+                for (int j = 0; j < UPS; ++j) map_unit<KID>(p, S, colw, wm, wn, lane, pv, pv.q + j);
+                pv.q += UPS;
+                ++it;
+                FX_GRAM_KSTEP_END();
+            }
+            for (; pv.q < UNITS; ++pv.q) map_unit<KID>(p, S, colw, wm, wn, lane, pv, pv.q);   // fewer k-steps than units
+            FX_GRAM_FINISH_PREV();
+        }
+        // phase 2: plain k-steps
+        for (; kt < KT; ++kt) {
+            FX_GRAM_KSTEP();
+            ++it;
+            FX_GRAM_KSTEP_END();
+        }
+
+        // drop the raw dot products into the staging tile (free once the store warps have sent the
+        // previous tile) and go on with the next tile
         mbar_wait(acc_empty, (tcount & 1) ^ 1);                  // passes at once for the first tile
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt) {
@@ -330,10 +392,29 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<double2*>(S + stage_off(r, c, u)) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_full);
+        // state of the tile now staged: norms (pre-scaled by -gamma), edge flag
+        pv.valid = true; pv.i0 = i0; pv.j0 = j0; pv.q = 0; pv.rs = pv.rs0 = 0.0;
+        {
+            const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
+            pv.edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) || (ig0 < j0 + BN && ig0 + BM > j0);
+        }
+        if (KID == 0) {
+            pv.ni0 = -p.km.p0 * p.na[i0 + wm * 64 + lane];
+            pv.ni1 = -p.km.p0 * p.na[i0 + wm * 64 + lane + 32];
+            colw[lane] = -p.km.p0 * p.nb[j0 + wn * 32 + lane];
+        }
+        __syncwarp();                                            // staging block and colw: this warp only
         ++tcount;
     }
+    // the last tile of this CTA has no successor to hide behind
+    if (pv.valid) {
+        if (pv.edge) map_edge_tile<KID>(p, S, colw, wm, wn, lane, pv);
+        for (; pv.q < UNITS; ++pv.q) map_unit<KID>(p, S, colw, wm, wn, lane, pv, pv.q);
+        FX_GRAM_FINISH_PREV();
+    }
+#undef FX_GRAM_FINISH_PREV
+#undef FX_GRAM_KSTEP
+#undef FX_GRAM_KSTEP_END
 }
 
 // ---- naive cross-check variant: one thread per output element -------------------------------
@@ -378,12 +459,23 @@ bool use_v3() {
     return v;
 }
 
+template <int KID, int UPS>
+int launch_ws2(fx_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmK,
+               const GramParams& p, unsigned grid) {
+    FX_SET_SMEM_ONCE(ctx, (gram_ws_kernel<KID, UPS>), SMEM_BYTES);
+    gram_ws_kernel<KID, UPS><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmK, p);
+    return 0;
+}
 template <int KID>
 int launch_ws(fx_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmK,
               const GramParams& p, unsigned grid) {
-    FX_SET_SMEM_ONCE(ctx, gram_ws_kernel<KID>, SMEM_BYTES);
-    gram_ws_kernel<KID><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmK, p);
-    return 0;
+    // units mapped per k-step: the map of the previous tile should be done after about half of the
+    // k-steps, so that the store warps have the other half to send it out
+    const int kt = p.kt;
+    if (kt >= 64) return launch_ws2<KID, 1>(ctx, tmA, tmB, tmK, p, grid);
+    if (kt >= 32) return launch_ws2<KID, 2>(ctx, tmA, tmB, tmK, p, grid);
+    if (kt >= 16) return launch_ws2<KID, 4>(ctx, tmA, tmB, tmK, p, grid);
+    return launch_ws2<KID, 8>(ctx, tmA, tmB, tmK, p, grid);
 }
 
 }  // namespace

@@ -465,6 +465,22 @@ __global__ void vec_axpy_kernel(long n, double a, const double* x, double* y) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += a * x[i];
 }
+__global__ void copy2d_add_kernel(const double* src, long lds, double* dst, long ldd, int rows, int cols) {
+    for (long idx = threadIdx.x + (long)blockIdx.x * blockDim.x; idx < (long)rows * cols;
+         idx += (long)blockDim.x * gridDim.x) {
+        const int i = (int)(idx % rows), j = (int)(idx / rows);
+        dst[i + j * ldd] += src[i + j * lds];
+    }
+}
+// one CTA: G[i][j] = Hs[mq + i][j] - sum_r Hs[r][i] Hs[r][j]
+__global__ void gram_downdate_kernel(const double* Hs, int ldh, int mq, int b, double* G) {
+    for (int idx = threadIdx.x; idx < b * b; idx += blockDim.x) {
+        const int i = idx % b, j = idx / b;
+        double s = 0.0;
+        for (int r = 0; r < mq; ++r) s = fma(Hs[r + (long)i * ldh], Hs[r + (long)j * ldh], s);
+        G[i + j * b] = Hs[mq + i + (long)j * ldh] - s;
+    }
+}
 __global__ void copy2d_kernel(const double* src, long lds, double* dst, long ldd, int rows, int cols) {
     for (long idx = threadIdx.x + (long)blockIdx.x * blockDim.x; idx < (long)rows * cols;
          idx += (long)blockDim.x * gridDim.x) {
@@ -477,6 +493,22 @@ __global__ void copy2d_kernel(const double* src, long lds, double* dst, long ldd
 int fx_launch_vec_axpy(fx_ctx* ctx, int64_t n, double a, const double* x, double* y) {
     if (n <= 0) return 0;
     vec_axpy_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, a, x, y);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_copy2d_add(fx_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd, int rows,
+                         int cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    copy2d_add_kernel<<<32, 256, 0, ctx->stream>>>(src, lds, dst, ldd, rows, cols);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
+}
+
+int fx_launch_gram_downdate(fx_ctx* ctx, const double* Hs, int ldh, int mq, int b, double* G) {
+    gram_downdate_kernel<<<1, 1024, 0, ctx->stream>>>(Hs, ldh, mq, b, G);
     ctx->launches++;
     FX_LAUNCH_CHECK();
     return 0;

@@ -68,7 +68,7 @@ size_t carve(fx_ctx* ctx, int64_t ld, int64_t n_ld, int k, const fx_solver_opts&
     double* Jw = take((size_t)mt * mt);
     double* theta = take(mt);
     double* H = take((size_t)mt * b);
-    double* H2 = take((size_t)mt * b);
+    double* H2 = take((size_t)(mt + b) * b);        // stacked [Q W]'W: mq coefficient rows + the b x b Gram
     double* G = take(64 * 64); double* Gs = take(64 * 64); double* U = take(64 * 64);
     double* Uw = take(64 * 64); double* lamb = take(64); double* dscale = take(64);
     double* M1 = take(64 * 64); double* C1 = take(64 * 64); double* M2 = take(64 * 64);
@@ -134,6 +134,37 @@ int project_out(fx_ctx* ctx, const Work& w, int mq, double* W, int64_t ld, doubl
     }
     tm.begin(&st->ortho_ms);
     FX_TRY(fx_launch_ts_nn(ctx, w.Q, mq, H, mq, b, -1.0, 1.0, W, ld, ld, variant));
+    tm.end();
+    return 0;
+}
+
+// One reduction for a re-projection and the block Gram matrix that follows it:
+//   Hs = [Q(:, :mq) W]' W  ((mq + b) x b, one all-reduce), then  G = W'W - H2'H2  is the Gram matrix
+// of W - Q H2 (Q orthonormal; H2 is a SECOND-pass coefficient block, tiny, so the subtraction does
+// not cancel), the block is orthonormalised from G (CholQR / SVQB) and  dst = (W - Q H2) M.
+// Saves one collective and one tall-skinny product per use against project_out + svqb_pass.
+int reproject_and_orthonormalise(fx_ctx* ctx, const Work& w, int mq, double* W, double* dst, int64_t ld,
+                                 double* Hs, double* Mout, double* Cout, int variant, FxTimer& tm, fx_stats* st) {
+    const int b = w.b, ldh = mq + b;
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_tn(ctx, w.Q, mq, W, b, ld, ld, Hs, ldh, w.tnscr, w.tnscr_doubles, variant));
+    FX_TRY(fx_launch_ts_tn(ctx, W, b, W, b, ld, ld, Hs + mq, ldh, w.tnscr, w.tnscr_doubles, variant));
+    tm.end();
+    if (ctx->world > 1) {
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allreduce_sum(ctx->comm, Hs, (size_t)ldh * b, ctx->stream));
+        tm.end();
+    }
+    tm.begin(&st->rr_ms);
+    FX_TRY(fx_launch_gram_downdate(ctx, Hs, ldh, mq, b, w.G));               // G = Hs[mq:, :] - H2'H2
+    FX_TRY(fx_launch_chol_factors(ctx, w.G, b, b, 1e-8, Mout, Cout, w.info + 6, w.info + 4));
+    FX_TRY(fx_launch_svqb_prep(ctx, w.G, b, b, w.Gs, w.dscale, w.info + 6));
+    FX_TRY(fx_launch_jacobi(ctx, w.Gs, b, b, w.U, b, w.lamb, w.Uw, w.info + 2, w.info + 6));
+    FX_TRY(fx_launch_svqb_factors(ctx, w.U, b, w.lamb, w.dscale, b, 1e-14, Mout, Cout, w.info + 4, w.info + 6));
+    tm.end();
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_nn(ctx, w.Q, mq, Hs, ldh, b, -1.0, 1.0, W, ld, ld, variant));     // W -= Q H2
+    FX_TRY(fx_launch_ts_nn(ctx, W, b, Mout, b, b, 1.0, 0.0, dst, ld, ld, variant));
     tm.end();
     return 0;
 }
@@ -207,16 +238,16 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
         if (!pending) FX_TRY(kv_pass(Qn, steps == 0));
         pending = false;
         steps++;
-        // 3-5. CGS2 against [Q Qn]; H accumulates both passes
+        // 3-5. CGS2 against [Q Qn]; H accumulates both passes.  The second pass shares its reduction
+        // with the Gram matrix of the block orthonormalisation (3 collectives per step, not 5).
         FX_TRY(project_out(ctx, w, mq, w.Wa, ld, w.H, variant, tm, st));
-        FX_TRY(project_out(ctx, w, mq, w.Wa, ld, nullptr, variant, tm, st));
-        FX_TRY(fx_launch_vec_axpy(ctx, (int64_t)mq * b, 1.0, w.H2, w.H));
+        FX_TRY(reproject_and_orthonormalise(ctx, w, mq, w.Wa, w.Wb, ld, w.H2, w.M1, w.C1, variant, tm, st));
+        FX_TRY(fx_launch_copy2d_add(ctx, w.H2, mq + b, w.H, mq, mq, b));          // H += H2 (leading mq rows)
         // 6. projected matrix
         FX_TRY(fx_launch_T_update(ctx, w.T, mt, w.H, mq, m, b));
-        // 7. SVQB, re-projection of the normalised block, SVQB again -> next block in place
-        FX_TRY(svqb_pass(ctx, w, w.Wa, w.Wb, ld, w.M1, w.C1, variant, tm, st));
-        FX_TRY(project_out(ctx, w, mq, w.Wb, ld, nullptr, variant, tm, st));
-        FX_TRY(svqb_pass(ctx, w, w.Wb, w.Q + (size_t)mq * ld, ld, w.M2, w.C2, variant, tm, st));
+        // 7. re-projection of the normalised block + second orthonormalisation -> next block in place
+        FX_TRY(reproject_and_orthonormalise(ctx, w, mq, w.Wb, w.Q + (size_t)mq * ld, ld, w.H2, w.M2, w.C2, variant,
+                                            tm, st));
         FX_TRY(fx_launch_small_matmul(ctx, w.C2, w.C1, b, w.C));
         m = mq;
         // 8. Rayleigh-Ritz on the side stream
