@@ -2,76 +2,67 @@
 // per-tile row sums fused behind the contraction.  Replaces MLKernels.kernelmatrix as called at
 // /root/reference/src/kpca.jl:51 (symmetric) and kpca.jl:65 (cross).
 //
-// One persistent CTA per SM, warp-specialised (512 threads, setmaxnreg 200 / 88 / 24):
-//   producer (warp 12, one lane): per 8-feature step TWO tensor-map bulk copies (TMA, SASS UTMALDG),
-//     boxes of {132 observations x 8 features} of the row and of the column operand -- the box is 4
-//     elements wider than the 128 it feeds, which makes the shared-memory row pitch 132 doubles and
-//     the LDS.64 fragment reads conflict free (t*132 + g distinct mod 16) -- into a 4-stage ring
-//     guarded by mbarrier full/empty pairs; it runs ahead across tile boundaries.
-//   8 MMA warps (2 x 4, 64 x 32 register tile each, DMMA.8x8x4 = mma.sync f64).  When a 128 x 128
-//     tile is done they drop the RAW dot products into a 128 KB staging tile in shared memory (the
-//     layout a 128-byte-swizzled TMA store expects) and start the next tile at once.  The kernel map
-//     of tile T (branch-free exp / templated powers / tanh, in place in the staging tile) is
-//     SOFTWARE-PIPELINED INTO THE MAIN LOOP OF TILE T+1: each k-step's 64 DMMAs share a basic block
-//     with the map of a few staged elements, so the map's FP64 operations fill the issue gaps of
-//     the DMMA stream instead of stopping it.  (DMMA and DFMA share one FP64 datapath.  Measured
-//     this round: a map that runs as a burst after each tile -- round 1, inside the MMA warps --
-//     leaves the datapath idle while both warps of a scheduler are in their bursts, 77-80 %; a map
-//     in separate epilogue warps is starved by the DMMA stream, the MMA warps end up waiting for
-//     the staging tile, 73-76 %.)
-//   4 store warps: when the MMA warps have mapped a tile, ONE tensor-map bulk store (UTMASTG) sends
-//     it to K; mirrored tiles are also written transposed, and the per-tile row / column sums that
-//     feed the centring are formed here.
+// Data path (persistent CTAs, 2 per SM, each looping over 128x64 output tiles):
+//   producer warpgroup (one active warp; gives its registers to the MMA warps via setmaxnreg):
+//     HBM --cp.async.bulk (TMA engine, UBLKCP) + mbarrier full/empty--> 3-stage smem ring of
+//     16-feature slabs; it runs ahead across tile boundaries.
+//   4 MMA warps: LDS.64 conflict-free (row stride = 4 mod 16 doubles) --> DMMA.8x8x4
+//     (mma.sync f64), 64x32 register tile per warp, no CTA-wide barrier in the main loop.
+//   epilogue, SOFTWARE-PIPELINED THROUGH TENSOR MEMORY: when a tile's contraction is done, each MMA
+//     warp parks its 64x32 block of raw dot products in TMEM (four tcgen05.st.32x32b.x32 per warp:
+//     lane L's 128 accumulator registers go to TMEM lane 32 (warp & 3) + L, 128 columns) and starts
+//     the next tile at once.  The kernel map of the parked tile (branch-free exp / templated powers /
+//     tanh), its row sums and its stores are then done two elements at a time (tcgen05.ld.x4) BETWEEN
+//     THE DMMAs OF THE NEXT TILE'S MAIN LOOP, a fixed number of units per k-step in the same basic
+//     block, so the map's FP64 operations (DMMA and DFMA share one datapath) fill issue gaps of the
+//     DMMA stream instead of stopping it.  fp64 has no tcgen05.mma, so on this path TMEM is otherwise
+//     idle: it serves as 128 KB/SM of register spill space with a one-instruction spill.
+//     What this replaces (measured, profiles/r02_gram_design_experiments.md): the map as a burst in
+//     the MMA warps after each tile (round 1) leaves the FP64 datapath idle whenever both warps of a
+//     scheduler are in their bursts: 77-80 % of the DMMA peak; the map in separate epilogue warps
+//     behind a shared-memory staging tile is starved by the DMMA stream and the 128 KB staging tile
+//     costs the operand ring its depth: 73-78 %.
+//   EDGE tiles (ragged borders, tiles touching the diagonal: O(n/128) of them) keep the burst
+//     epilogue with validity masks and the same-point test.
 //
 // Symmetry.  K is symmetric when A is a row block of B.  sym = 1 (one rank, or no peer access):
 // inside this rank's square diagonal block only the tiles on / right of the diagonal are computed
-// and the strictly-right ones are mirrored: the epilogue thread that owns tile row r writes its
-// mapped values down column r of the transposed tile, so a warp's store instruction covers 32
-// consecutive doubles (256 contiguous bytes) of one row of the mirrored tile.  sym = 2 (several
-// ranks, peer arenas mapped through CUDA IPC): the off-diagonal blocks are shared out too -- of
-// each pair of blocks (r,c) / (c,r) exactly one rank computes every tile and stores the transposed
-// values, and the column sums that are the peer's row-sum partials, STRAIGHT INTO THE PEER'S K
-// over NVLink (st.global to the IPC-mapped address), so every rank executes ~half of its row
-// block and no separate exchange step exists.
-#include <cuda.h>
+// and the strictly-right ones are mirrored by transposed stores from the fragments.  sym = 2
+// (several ranks, peer arenas mapped through CUDA IPC): the off-diagonal blocks are shared out
+// too -- of each pair of blocks (r,c) / (c,r) exactly one rank computes every 128x128 super-tile
+// and stores the transposed values, and the column sums that are the peer's row-sum partials,
+// STRAIGHT INTO THE PEER'S K over NVLink (512-byte cp.async.bulk stores from a per-warp transposition
+// buffer to the IPC-mapped address), so every rank executes ~half of its row block and no separate
+// exchange step exists.
 #include <stdlib.h>
 #include "fx_kernels.cuh"
 #include "gram_tiles.cuh"
 
-int fx_launch_gram_v3(fx_ctx* ctx, const GramArgs& a, int variant);      // gram_v3.cu
+int fx_launch_gram_v3(fx_ctx* ctx, const GramArgs& a, int variant);      // gram_v3.cu (A/B only)
 
 namespace {
 
-constexpr int BM = FX_GRAM_BM, BN = FX_GRAM_BN, BK = 8, NST = 4;
-constexpr int PITCH = 132;                                   // doubles per staged operand row
-constexpr int SLAB_BYTES = BK * PITCH * 8;                   // 8448 (multiple of 128)
-constexpr int STAGE_BYTES = 2 * SLAB_BYTES;
-constexpr int ACC_BYTES = BM * BN * 8;                       // 131072: the staging tile
-constexpr int OFF_STAGES = ACC_BYTES;
-constexpr int OFF_COLW = OFF_STAGES + NST * STAGE_BYTES;     // [8 warps][32] pre-scaled column norms of the staged tile
-constexpr int OFF_RSUM = OFF_COLW + 8 * 32 * 8;              // [8 warps][64] row sums of each warp's 64 x 32 block
-constexpr int OFF_BARS = OFF_RSUM + 8 * 64 * 8;
-constexpr int SMEM_BYTES = OFF_BARS + 128 + 1024;            // + slack for the 1024-byte alignment
-constexpr int NTHREADS = 512;                                // 8 MMA + 4 store + 4 producer-group warps
-constexpr int ST_THREADS = 128, ST_TID0 = 256;
-constexpr int UNITS = 32;                                    // 16-byte units (2 elements) per lane per tile
-constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
-constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+constexpr int BM = FX_GRAM_BM, BN = FX_GRAM_BN, BK = 16, STAGES = 3;
+constexpr int AS = BM + 4;                      // 132: (t*AS + g) mod 16 distinct for t,g in 0..3
+constexpr int BS = BN + 4;                      // 68
+constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25600 B)
+// mirror staging: per MMA warp two buffers of 8 transposed rows x 64 (+2 pad: conflict-free
+// 8-byte stores for lanes (g,t) -> word (2t+q)*TS + g) -- sent off with 512-byte bulk stores
+constexpr int TS = 66, TBUF_D = 8 * TS;
+constexpr int UNITS = 32;                       // (mt, nt) accumulator pairs per lane per tile
+// smem (doubles): stages | rs [2 bufs][2 halves][BM] | 16 (barriers + TMEM base) | tstage | rowacc [4 warps][8][32]
+constexpr int OFF_RS = STAGES * STAGE_D;
+constexpr int OFF_BAR = OFF_RS + 4 * BM;
+constexpr int OFF_TST = OFF_BAR + 16;
+constexpr int OFF_RACC = OFF_TST + 4 * 2 * TBUF_D;
+constexpr int SMEM_BYTES = (OFF_RACC + 4 * 8 * 32) * 8;
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
-    return fn;
+// 1-D bulk store shared -> global (TMA engine); the destination may be a peer GPU's memory
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                     __cvta_generic_to_global(dst_gmem)),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
 }
 
 struct GramParams {
@@ -92,28 +83,45 @@ struct GramParams {
 
 // tile_role() / tile_coords(): gram_tiles.cuh (host-testable)
 
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar,
-                                            uint64_t hint) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(hint)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2,
-                                             uint64_t hint) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(
-            reinterpret_cast<uint64_t>(tm)),
-        "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)), "l"(hint)
-        : "memory");
-}
-__device__ __forceinline__ void bar_sync_store() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// Byte offset of the 16-byte unit that holds columns (2u', 2u'+1) of chunk `c` in row `r` of the
-// staging tile: [chunk of 16 columns][row][128 bytes], the eight 16-byte units of a row XOR-swizzled
-// with (row & 7) -- the shared-memory image of a {16, 128, 8} box of a SWIZZLE_128B tensor map.
-__device__ __forceinline__ int stage_off(int r, int c, int u) { return c * (BM * 128) + r * 128 + ((u ^ (r & 7)) << 4); }
+// ---- tensor memory as accumulator spill space -------------------------------------------------
+// One instruction parks a lane's 64 accumulators (128 x 32-bit registers) in TMEM: lane L of warp w
+// owns TMEM lane 32 (w & 3) + L; accumulator pair (mt, nt) sits at columns 4 (4 mt + nt) .. + 3.
+// (Issued as four .x32 pieces: ptxas allocates the operand block of a TMEM store against the
+// kernel's LAUNCH register target -- 128 with two CTAs per SM -- not against the setmaxnreg budget.)
+__device__ __forceinline__ void tmem_park32(uint32_t taddr, const uint32_t* r) {
+#define R8(i) "r"(r[i]), "r"(r[i + 1]), "r"(r[i + 2]), "r"(r[i + 3]), "r"(r[i + 4]), "r"(r[i + 5]), "r"(r[i + 6]), "r"(r[i + 7])
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {"
+        "%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), R8(0), R8(8), R8(16), R8(24)
+        : "memory");
+#undef R8
+}
+__device__ __forceinline__ void tmem_park(uint32_t taddr, const double (&acc)[8][4][2]) {
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = part * 16 + i;                        // element (mt, nt, q) in storage order
+            const double v = acc[e >> 3][(e >> 1) & 3][e & 1];
+            r[2 * i] = (uint32_t)__double2loint(v);
+            r[2 * i + 1] = (uint32_t)__double2hiint(v);
+        }
+        tmem_park32(taddr + 32 * part, r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double2 tmem_fetch2(uint32_t taddr) {
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return make_double2(__hiloint2double((int)b, (int)a), __hiloint2double((int)d, (int)c));
+}
 
 // Map of one element; for the Gaussian kernel (KID 0) the norms arrive pre-scaled by -gamma.
 template <int KID>
@@ -122,97 +130,275 @@ __device__ __forceinline__ double gram_map(const KernelMap& km, double dot, doub
     return kernel_map_t<KID>(km, dot, ni, nj, same);
 }
 
-// Geometry of the in-place map: MMA warp (wm, wn) maps the 64 x 32 block it produced.  Lane L owns
-// rows wm*64 + L and wm*64 + L + 32 and walks the 16 units (2 chunks x 8) of each: unit q = 0..31 is
-// row L + 32 (q >> 4), chunk wn*2 + ((q >> 3) & 1), unit q & 7.  Lanes = consecutive rows, so the
-// swizzle makes every quarter-warp hit 8 distinct 16-byte units: conflict free.
-struct PrevTile {
-    long i0, j0;            // coordinates of the tile that sits (raw) in the staging tile
-    int q;                  // next unit to map (UNITS = done)
-    bool valid, edge;
-    double ni0, ni1;        // pre-scaled norms of this lane's two rows (Gaussian)
-    double rs, rs0;         // running row sum of the mapped values (this warp's 32 columns); rs0 = first row's
-                            // (scalars, no arrays: a run-time index would put the struct in local memory)
+// ---- the parked tile ------------------------------------------------------------------------------
+// Scalars only (a run-time index into a member array would put the struct in local memory).
+struct Parked {
+    long i0, j0;            // tile coordinates
+    int tx;                 // tile-column index (row-sum slot)
+    int q;                  // next unit (UNITS = done); unit q is accumulator pair (mt = q & 7, nt = q >> 3)
+    bool valid, mirror;
+    double* Kmir;           // mirror target: K / rowpart of the owner of the transposed tile, its first row
+    double* rpmir;
+    long mir_row0;
+    double cs0, cs1;        // running column sums of the current 8-column group (mirror)
 };
 
-template <int KID>
-__device__ __forceinline__ void map_unit(const GramParams& p, unsigned char* S, const double* colw, int wm, int wn,
-                                         int lane, PrevTile& pv, int q) {
-    const int rsel = q >> 4, c = wn * 2 + ((q >> 3) & 1), u = q & 7;
-    double2* ptr = reinterpret_cast<double2*>(S + stage_off(wm * 64 + lane + 32 * rsel, c, u));
-    const double2 dv = *ptr;
-    double n0 = 0.0, n1 = 0.0;
+// One unit of the parked tile: fetch the raw dot products of accumulator pair (mt, nt) from TMEM,
+// map, store, add to the row-sum slot; MIRROR tiles also stage the transposed values and, at the end
+// of each 8-column group, send 8 transposed rows (512-byte bulk stores) and the group's column sums.
+// Interior tiles only: no masks, no same-point test.
+template <int KID, bool MIRROR>
+__device__ __forceinline__ void parked_unit(const GramParams& p, Parked& pk, int q, uint32_t taddr, int wm, int wn, int g,
+                                            int t, int lane, double* racc, double* tbuf) {
+    const int mt = q & 7, nt = q >> 3;
+    const double2 raw = tmem_fetch2(taddr + 4 * (4 * mt + nt));
+    const long i = pk.i0 + wm * 64 + mt * 8 + g;
+    const long jb = pk.j0 + wn * 32 + nt * 8 + 2 * t;
+    double ni = 0.0, nb0 = 0.0, nb1 = 0.0;
     if (KID == 0) {
-        const double2 nn = *reinterpret_cast<const double2*>(colw + (q & 15) * 2);         // broadcast read
-        n0 = nn.x; n1 = nn.y;
+        ni = -p.km.p0 * __ldg(p.na + i);
+        const double2 v = __ldg(reinterpret_cast<const double2*>(p.nb + jb));
+        nb0 = -p.km.p0 * v.x; nb1 = -p.km.p0 * v.y;
     }
-    const double ni = rsel ? pv.ni1 : pv.ni0;
-    const double v0 = gram_map<KID>(p.km, dv.x, ni, n0, false);
-    const double v1 = gram_map<KID>(p.km, dv.y, ni, n1, false);
-    *ptr = make_double2(v0, v1);
-    if (q == 16) { pv.rs0 = pv.rs; pv.rs = 0.0; }              // second row starts
-    pv.rs += v0 + v1;
+    const double v0 = gram_map<KID>(p.km, raw.x, ni, nb0, false);
+    const double v1 = gram_map<KID>(p.km, raw.y, ni, nb1, false);
+    *reinterpret_cast<double2*>(p.K + i * p.ldk + jb) = make_double2(v0, v1);
+    racc[mt * 32 + lane] += v0 + v1;                            // this lane's private slot
+    if (MIRROR) {
+        double* tb = tbuf + (nt & 1) * TBUF_D;
+        if (mt == 0 && nt >= 2) {
+            // the bulk stores issued from this buffer two groups ago must have read it
+            if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        tb[(2 * t) * TS + mt * 8 + g] = v0;                     // transposed: row = column of the tile
+        tb[(2 * t + 1) * TS + mt * 8 + g] = v1;
+        pk.cs0 += v0;
+        pk.cs1 += v1;
+        if (mt == 7) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < 8) {
+                // transposed row j = j0 + wn*32 + nt*8 + lane, columns [i0 + wm*64, +64) of the owner's block
+                double* dst = pk.Kmir + (pk.j0 + wn * 32 + nt * 8 + lane - pk.mir_row0) * p.ldk + pk.i0 + wm * 64 + p.diag_shift;
+                bulk_s2g(dst, tb + lane * TS, 64 * 8);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (pk.rpmir) {
+                // column sums over this warp's 64 rows = row-sum partial of mirrored row j for the
+                // 64-column slot [i0 + wm*64, +64) of that row: slot index = 2*(i0/BM) + wm
+                const long slot = p.diag_shift / BN + 2 * (pk.i0 / BM) + wm;
+                double cs0 = pk.cs0, cs1 = pk.cs1;
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+                if (g == 0) {
+                    double* r = pk.rpmir + slot * p.rows_pad + (jb - pk.mir_row0);
+                    *reinterpret_cast<double2*>(r) = make_double2(cs0, cs1);
+                }
+            }
+            pk.cs0 = pk.cs1 = 0.0;
+        }
+    }
 }
 
-// EDGE tiles (ragged borders or touching the diagonal): validity masks and the same-point test;
-// mapped in one go before the main loop of the next tile (they are O(n / 128) of O((n / 128)^2) tiles).
-template <int KID>
-__device__ __forceinline__ void map_edge_tile(const GramParams& p, unsigned char* S, const double* colw, int wm, int wn,
-                                           int lane, PrevTile& pv) {
-    for (int q = pv.q; q < UNITS; ++q) {
-        const int rsel = q >> 4, c = wn * 2 + ((q >> 3) & 1), u = q & 7;
-        const int row = wm * 64 + lane + 32 * rsel;
-        double2* ptr = reinterpret_cast<double2*>(S + stage_off(row, c, u));
-        const double2 dv = *ptr;
-        double n0 = 0.0, n1 = 0.0;
-        if (KID == 0) { n0 = colw[(q & 15) * 2]; n1 = colw[(q & 15) * 2 + 1]; }
-        const long i = pv.i0 + row, j = pv.j0 + c * 16 + u * 2;
+// All units of the parked tile are done: drain the mirror stores, fold the per-lane row-sum slots
+// (over the four t lanes), and -- after the 4 MMA warps met -- write the tile's row-sum partials.
+__device__ __forceinline__ void parked_finish(const GramParams& p, Parked& pk, int wm, int wn, int g, int t, int lane,
+                                              int tid, double* racc, double* rsb) {
+    if (pk.mirror) {
+        if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+        double v = racc[mt * 32 + lane];
+        racc[mt * 32 + lane] = 0.0;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = v;
+    }
+    if (p.rowpart) {
+        bar_sync_compute();                  // both column halves of every row are in smem
+        p.rowpart[(long)pk.tx * p.rows_pad + pk.i0 + tid] = rsb[tid] + rsb[BM + tid];
+    }
+    pk.valid = false;
+}
+
+// Kernel map + row sums + stores for one warp's 64x32 accumulator tile.  EDGE tiles (ragged
+// borders or touching the diagonal) carry the validity masks and the same-point test; interior
+// tiles run the bare arithmetic.
+template <int KID, bool EDGE>
+__device__ __forceinline__ void gram_epilogue_plain(const GramParams& p, double (&acc)[8][4][2],
+                                                    const double (&ni)[8], const double (&nbv)[4][2], long i0,
+                                                    long j0, int wm, int wn, int g, int t, double* rsb) {
+    const long jb = j0 + wn * 32 + 2 * t;
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+        const long i = i0 + wm * 64 + mt * 8 + g;
+        double* krow = p.K + i * p.ldk + jb;
         const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
         const bool iv = i < p.rows_valid;
-        const double ni = rsel ? pv.ni1 : pv.ni0;
-        double v0 = gram_map<KID>(p.km, dv.x, ni, n0, ig == j);
-        double v1 = gram_map<KID>(p.km, dv.y, ni, n1, ig == j + 1);
-        v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
-        v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
-        *ptr = make_double2(v0, v1);
-        if (q == 16) { pv.rs0 = pv.rs; pv.rs = 0.0; }
-        pv.rs += v0 + v1;
+        double sacc = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            double v0, v1;
+            if (EDGE) {
+                const long j = jb + nt * 8;
+                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], ig == j);
+                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], ig == j + 1);
+                v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
+                v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
+            } else {
+                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nbv[nt][0], false);
+                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nbv[nt][1], false);
+            }
+            *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(v0, v1);
+            sacc += v0 + v1;
+        }
+        if (p.rowpart) {
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = sacc;
+        }
     }
-    pv.q = UNITS;
 }
 
-// UPS = staged units mapped per k-step while a previous tile is pending (chosen by the launcher so
-// that the map is finished after about half of the k-steps: 32 / UPS <= kt / 2 where possible).
+// The same for MIRROR tiles (symmetric mode): also sends the transposed tile to its owner.
+template <int KID, bool EDGE>
+__device__ __forceinline__ void gram_epilogue_mirror(const GramParams& p, double (&acc)[8][4][2],
+                                              const double (&ni)[8], long i0,
+                                              long j0, int wm, int wn, int g, int t, double* rsb,
+                                              double* Kmir, double* rpmir, long mir_row0, double* tbuf) {
+    // Kmir / rpmir: K and rowpart of the rank that owns rows [mir_row0, +rows_pad) -- this rank
+    // itself inside the diagonal block, a peer (NVLink) for the shared-out blocks.  The mirrored
+    // values go through a small transposed staging buffer (tbuf: 2 x [8][TS] per warp) and leave
+    // as 512-byte bulk stores, 8 per 8-column group: direct transposed stores from the fragments
+    // are 64-byte pieces, which NVLink carries at a fraction of its bandwidth.
+    const long jb = j0 + wn * 32 + 2 * t;
+    const int lane = g * 4 + t;
+    double sacc[8];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) sacc[mt] = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        double* tb = tbuf + (nt & 1) * TBUF_D;
+        double cs0 = 0.0, cs1 = 0.0;
+        // column norms re-read per group (L1 hit): keeps 12 registers free for the row sums
+        double nb0 = 0.0, nb1 = 0.0;
+        if (KID == 0) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(p.nb + jb + nt * 8));
+            nb0 = -p.km.p0 * v.x; nb1 = -p.km.p0 * v.y;
+        }
+        if (nt >= 2) {
+            // the bulk stores issued from this buffer two groups ago must have read it
+            if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+            const long i = i0 + wm * 64 + mt * 8 + g;
+            double v0, v1;
+            if (EDGE) {
+                const long ig = (p.diag_shift >= 0) ? i + p.diag_shift : -1;
+                const bool iv = i < p.rows_valid;
+                const long j = jb + nt * 8;
+                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, ig == j);
+                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, ig == j + 1);
+                v0 = (iv && j < p.cols_valid) ? v0 : 0.0;
+                v1 = (iv && j + 1 < p.cols_valid) ? v1 : 0.0;
+            } else {
+                v0 = gram_map<KID>(p.km, acc[mt][nt][0], ni[mt], nb0, false);
+                v1 = gram_map<KID>(p.km, acc[mt][nt][1], ni[mt], nb1, false);
+            }
+            *reinterpret_cast<double2*>(p.K + i * p.ldk + jb + nt * 8) = make_double2(v0, v1);
+            tb[(2 * t) * TS + mt * 8 + g] = v0;              // transposed: row = column of the tile
+            tb[(2 * t + 1) * TS + mt * 8 + g] = v1;
+            cs0 += v0;
+            cs1 += v1;
+            sacc[mt] += v0 + v1;
+        }
+        {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < 8) {
+                // transposed row j = j0 + wn*32 + nt*8 + lane, columns [i0 + wm*64, +64) of the owner's block
+                double* dst = Kmir + (j0 + wn * 32 + nt * 8 + lane - mir_row0) * p.ldk + i0 + wm * 64 + p.diag_shift;
+                bulk_s2g(dst, tb + lane * TS, 64 * 8);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (rpmir) {
+                // column sums over this warp's 64 rows = row-sum partial of mirrored row j for the
+                // 64-column slot [i0 + wm*64, +64) of that row: slot index = 2*(i0/BM) + wm
+                const long slot = p.diag_shift / BN + 2 * (i0 / BM) + wm;
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+                cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16);
+                cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+                if (g == 0) {
+                    double* r = rpmir + slot * p.rows_pad + (jb - mir_row0) + nt * 8;
+                    *reinterpret_cast<double2*>(r) = make_double2(cs0, cs1);
+                }
+            }
+        }
+    }
+    {
+        // both staging buffers free again before the next tile touches them
+        if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+    }
+    if (p.rowpart) {
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+            double v = sacc[mt];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = v;
+        }
+    }
+}
+
+// UPS = parked units handled per k-step (32 / UPS k-steps finish the parked tile; the launcher picks
+// the smallest UPS in {1, 2, 4, 8} with UPS * kt >= 32, left-overs are handled after the main loop).
 template <int KID, int UPS>
-__global__ void __launch_bounds__(NTHREADS, 1)
-gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmK, const GramParams p) {
-    extern __shared__ unsigned char smem_dyn[];
-    // 1024-byte alignment by pointer arithmetic on the __shared__ array itself (a round trip through
-    // an integer makes the compiler lose the address space and emit generic LD / ST)
-    unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    unsigned char* S = base;                                       // staging tile (1024-byte aligned)
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + OFF_BARS);
-    uint64_t* empty = full + NST;
-    uint64_t* mapped = empty + NST;                                // staging tile holds K values (8 MMA warps arrive)
-    uint64_t* acc_empty = mapped + 1;                              // staging tile has been stored (store warps arrive)
+__global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(smem_raw);
+    double* rs = smem + OFF_RS;                                    // [2 bufs][2 halves][BM]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* empty = full + STAGES;
+    uint32_t* tmem_base = reinterpret_cast<uint32_t*>(empty + STAGES);
+    double* tstage = smem + OFF_TST;
+    double* racc_all = smem + OFF_RACC;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
     const int KT = p.kt;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
-        mbar_init(mapped, 8);
-        mbar_init(acc_empty, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
         fence_mbar_init();
     }
+    if (warp == 0) {
+        // 128 TMEM columns for the 4 MMA warps of this CTA (two CTAs per SM: 256 of 512 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = tid; i < 4 * 8 * 32; i += 256) racc_all[i] = 0.0;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    if (warp >= 12) {
-        // ------------------------------ producer warpgroup ------------------------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (warp != 12 || lane != 0) return;
+    if (warp >= 4) {
+        // ---------------- producer warpgroup: hands its registers to the MMA warps ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp != 4) return;
         int it = 0;
         for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             long i0, j0; int tx;
@@ -220,201 +406,161 @@ gram_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int peer;
             if (tile_role(p, (int)(i0 / BM), tx, peer) == 0) continue;      // produced by a mirror store
             for (int kt = 0; kt < KT; ++kt, ++it) {
-                const int s = it & (NST - 1);
-                mbar_wait(&empty[s], ((it / NST) & 1) ^ 1);       // passes at once on first use
-                unsigned char* st = base + OFF_STAGES + s * STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-                tma_load_2d(st, &tmA, (int)i0, kt * BK, &full[s], L2_EVICT_LAST);
-                tma_load_2d(st + SLAB_BYTES, &tmB, (int)j0, kt * BK, &full[s], L2_EVICT_LAST);
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);    // passes at once on first use
+                double* As = smem + (size_t)s * STAGE_D;
+                double* Bs = As + BK * AS;
+                if (lane == 0) mbar_arrive_expect_tx(&full[s], BK * (BM + BN) * 8);
+                __syncwarp();
+                if (lane < BK)
+                    bulk_g2s(As + lane * AS, p.A + (long)(kt * BK + lane) * p.lda + i0, BM * 8, &full[s]);
+                else
+                    bulk_g2s(Bs + (lane - BK) * BS, p.B + (long)(kt * BK + lane - BK) * p.ldb + j0, BN * 8,
+                             &full[s]);
             }
         }
-        return;
-    }
-
-    if (warp >= 8) {
-        // ------------------------------ store warpgroup ------------------------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-        const int e = tid - ST_TID0;                               // tile row (pass 1) / tile column (pass 2)
-        const double* rsum_w = reinterpret_cast<const double*>(base + OFF_RSUM);
-        int tcount = 0;
-        for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
-            long i0, j0; int tx;
-            tile_coords(p, tile, i0, j0, tx);
-            int peer;
-            const int role = tile_role(p, (int)(i0 / BM), tx, peer);
-            if (role == 0) continue;
-            mbar_wait(mapped, tcount & 1);                         // the MMA warps finished the map of this tile
-            if (e == 0) {
-                tma_store_3d(&tmK, S, 0, (int)i0, (int)(j0 / 16), L2_EVICT_FIRST);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            if (p.rowpart) {
-                // row-sum partials, one slot per 64 columns: the four column blocks of the MMA warps, pairwise
-                const int wm = e >> 6, r = e & 63;
-                const double* rw = rsum_w + (wm * 4) * 64 + r;
-                p.rowpart[(long)(2 * tx) * p.rows_pad + i0 + e] = rw[0] + rw[64];
-                p.rowpart[(long)(2 * tx + 1) * p.rows_pad + i0 + e] = rw[128] + rw[192];
-            }
-            if (role == 2) {
-                double* Kmir = (p.sym == 2) ? p.peerK[peer] : p.K;
-                double* rpmir = (p.sym == 2) ? p.peerRowpart[peer] : p.rowpart;
-                const long mir_row0 = (p.sym == 2) ? (long)peer * p.rows_pad : p.diag_shift;
-                // transposed tile: thread e walks row e of the staging tile and writes column
-                // (i0 + e) of the owner's rows j0 - mir_row0 + ..: lanes = consecutive columns, so a
-                // warp's store covers 256 contiguous bytes of one mirrored row
-                double* mir = Kmir + (j0 - mir_row0) * p.ldk + (i0 + e + p.diag_shift);
-#pragma unroll 1
-                for (int c = 0; c < BN / 16; ++c) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const double2 v = *reinterpret_cast<const double2*>(S + stage_off(e, c, u));
-                        const int col = c * 16 + u * 2;
-                        __stcs(mir + (long)col * p.ldk, v.x);
-                        __stcs(mir + (long)(col + 1) * p.ldk, v.y);
-                    }
-                }
-                if (rpmir) {
-                    // column sums = row-sum partials of the mirrored rows; thread e sums column e over
-                    // the tile rows [0, 64) and [64, 128): columns [i0, +64), [i0 + 64, +64) of the owner
-                    const int c = e >> 4, u = (e & 15) >> 1, hb = (e & 1) * 8;
-                    double cs0 = 0.0, cs1 = 0.0;
-#pragma unroll 8
-                    for (int r = 0; r < 64; ++r) {
-                        cs0 += *reinterpret_cast<const double*>(S + stage_off(r, c, u) + hb);
-                        cs1 += *reinterpret_cast<const double*>(S + stage_off(r + 64, c, u) + hb);
-                    }
-                    const long slot = (i0 + p.diag_shift) / 64;
-                    rpmir[slot * p.rows_pad + (j0 - mir_row0) + e] = cs0;
-                    rpmir[(slot + 1) * p.rows_pad + (j0 - mir_row0) + e] = cs1;
-                }
-            }
-            if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            bar_sync_store();                                      // store engine and all readers are done with S
-            if (e == 0) mbar_arrive(acc_empty);
-            ++tcount;
-        }
-        if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         return;
     }
 
     // -------------------------------- MMA warps --------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
-    double* colw = reinterpret_cast<double*>(base + OFF_COLW) + warp * 32;
-    double* rsum_w = reinterpret_cast<double*>(base + OFF_RSUM) + warp * 64;
-    PrevTile pv;
-    pv.valid = false; pv.edge = false; pv.q = UNITS; pv.i0 = pv.j0 = 0;
-    pv.ni0 = pv.ni1 = pv.rs = pv.rs0 = 0.0;
-    int it = 0, tcount = 0;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int wm = warp >> 1, wn = warp & 1;
+    const uint32_t taddr = *tmem_base + ((uint32_t)(32 * warp) << 16);      // this warp's TMEM lane quarter
+    double* racc = racc_all + warp * (8 * 32);
+    double* tbuf = tstage + warp * 2 * TBUF_D;
+    Parked pk;
+    pk.valid = false; pk.mirror = false; pk.q = UNITS; pk.i0 = pk.j0 = 0; pk.tx = 0;
+    pk.Kmir = nullptr; pk.rpmir = nullptr; pk.mir_row0 = 0; pk.cs0 = pk.cs1 = 0.0;
+    int it = 0, fin = 0;
 
-    // signals that the staged tile is mapped: row sums out, staging writes ordered before the TMA store
-#define FX_GRAM_FINISH_PREV()                                                                                    \
+#define FX_GRAM_KSTEP()                                                                                          \
     {                                                                                                            \
-        rsum_w[lane] = pv.rs0;                                                                                   \
-        rsum_w[lane + 32] = pv.rs;                                                                               \
-        fence_proxy_async();                                                                                     \
+        const int s = it % STAGES;                                                                               \
+        mbar_wait(&full[s], (it / STAGES) & 1);                                                                  \
+        const double* As = smem + (size_t)s * STAGE_D + wm * 64 + g;                                             \
+        const double* Bs = smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g;                                   \
+        _Pragma("unroll")                                                                                        \
+        for (int kk = 0; kk < BK / 4; ++kk) {                                                                    \
+            double a[8], b[4];                                                                                   \
+            const int kr = kk * 4 + t;                                                                           \
+            _Pragma("unroll")                                                                                    \
+            for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * AS + mt * 8];                                         \
+            _Pragma("unroll")                                                                                    \
+            for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * BS + nt * 8];                                         \
+            _Pragma("unroll")                                                                                    \
+            for (int mt = 0; mt < 8; ++mt)                                                                       \
+                _Pragma("unroll")                                                                                \
+                for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);               \
+        }                                                                                                        \
+    }
+#define FX_GRAM_KSTEP_END()                                                                                      \
+    {                                                                                                            \
         __syncwarp();                                                                                            \
-        if (lane == 0) mbar_arrive(mapped);                                                                      \
-        pv.valid = false;                                                                                        \
+        if (lane == 0) mbar_arrive(&empty[(it - 1) % STAGES]);          /* this warp is done with the stage */   \
     }
 
     for (long tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         long i0, j0; int tx;
         tile_coords(p, tile, i0, j0, tx);
         int peer;
-        if (tile_role(p, (int)(i0 / BM), tx, peer) == 0) continue;
-        if (pv.valid && pv.edge) map_edge_tile<KID>(p, S, colw, wm, wn, lane, pv);   // before the accumulators are live
+        const int role = tile_role(p, (int)(i0 / BM), tx, peer);
+        if (role == 0) continue;
+        const bool mirror = role == 2;
         double acc[8][4][2];
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-        // one k-step: 64 DMMAs on stage (it mod NST)
-#define FX_GRAM_KSTEP()                                                                                          \
-        {                                                                                                        \
-            const int s = it & (NST - 1);                                                                        \
-            mbar_wait(&full[s], (it / NST) & 1);                                                                 \
-            const double* As = reinterpret_cast<const double*>(base + OFF_STAGES + s * STAGE_BYTES) + wm * 64 + g; \
-            const double* Bs = reinterpret_cast<const double*>(base + OFF_STAGES + s * STAGE_BYTES + SLAB_BYTES) + wn * 32 + g; \
-            _Pragma("unroll")                                                                                    \
-            for (int kk = 0; kk < BK / 4; ++kk) {                                                                \
-                double a[8], b[4];                                                                               \
-                const int kr = kk * 4 + t;                                                                       \
-                _Pragma("unroll")                                                                                \
-                for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * PITCH + mt * 8];                                  \
-                _Pragma("unroll")                                                                                \
-                for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * PITCH + nt * 8];                                  \
-                _Pragma("unroll")                                                                                \
-                for (int mt = 0; mt < 8; ++mt)                                                                   \
-                    _Pragma("unroll")                                                                            \
-                    for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);           \
-            }                                                                                                    \
-        }
-#define FX_GRAM_KSTEP_END()                                                                                      \
-        {                                                                                                        \
-            __syncwarp();                                                                                        \
-            if (lane == 0) mbar_arrive(&empty[(it - 1) & (NST - 1)]);                                            \
-        }
-
         int kt = 0;
-        if (pv.valid) {
-            // phase 1: k-steps that also map UPS staged units of the previous tile (same basic block
-            // as the DMMAs: the scheduler interleaves the map's instructions with them)
-            for (; kt < KT && pv.q < UNITS; ++kt) {
-                FX_GRAM_KSTEP();
+        if (pk.valid) {
+            // k-steps that also take UPS units of the parked tile (same basic block as the DMMAs)
+            if (pk.mirror) {
+                for (; kt < KT && pk.q < UNITS; ++kt) {
+                    FX_GRAM_KSTEP();
 #pragma unroll
-                for (int j = 0; j < UPS; ++j) map_unit<KID>(p, S, colw, wm, wn, lane, pv, pv.q + j);
-                pv.q += UPS;
-                ++it;
-                FX_GRAM_KSTEP_END();
+                    for (int j = 0; j < UPS; ++j) parked_unit<KID, true>(p, pk, pk.q + j, taddr, wm, wn, g, t, lane, racc, tbuf);
+                    pk.q += UPS;
+                    ++it;
+                    FX_GRAM_KSTEP_END();
+                }
+            } else {
+                for (; kt < KT && pk.q < UNITS; ++kt) {
+                    FX_GRAM_KSTEP();
+#pragma unroll
+                    for (int j = 0; j < UPS; ++j) parked_unit<KID, false>(p, pk, pk.q + j, taddr, wm, wn, g, t, lane, racc, tbuf);
+                    pk.q += UPS;
+                    ++it;
+                    FX_GRAM_KSTEP_END();
+                }
             }
-            for (; pv.q < UNITS; ++pv.q) map_unit<KID>(p, S, colw, wm, wn, lane, pv, pv.q);   // fewer k-steps than units
-            FX_GRAM_FINISH_PREV();
         }
-        // phase 2: plain k-steps
         for (; kt < KT; ++kt) {
             FX_GRAM_KSTEP();
             ++it;
             FX_GRAM_KSTEP_END();
         }
+        if (pk.valid) {
+            // fewer k-steps than the parked tile needed (small d): the rest in one go
+            for (; pk.q < UNITS; ++pk.q) {
+                if (pk.mirror) parked_unit<KID, true>(p, pk, pk.q, taddr, wm, wn, g, t, lane, racc, tbuf);
+                else           parked_unit<KID, false>(p, pk, pk.q, taddr, wm, wn, g, t, lane, racc, tbuf);
+            }
+            parked_finish(p, pk, wm, wn, g, t, lane, tid, racc, rs + (fin & 1) * 2 * BM);
+            ++fin;
+        }
 
-        // drop the raw dot products into the staging tile (free once the store warps have sent the
-        // previous tile) and go on with the next tile
-        mbar_wait(acc_empty, (tcount & 1) ^ 1);                  // passes at once for the first tile
+        const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
+        const bool edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) ||
+                          (ig0 < j0 + BN && ig0 + BM > j0);
+        double* Kmir = nullptr; double* rpmir = nullptr; long mir_row0 = 0;
+        if (mirror) {
+            Kmir = (p.sym == 2) ? p.peerK[peer] : p.K;
+            rpmir = (p.sym == 2) ? p.peerRowpart[peer] : p.rowpart;
+            mir_row0 = (p.sym == 2) ? (long)peer * p.rows_pad : p.diag_shift;
+        }
+        if (edge) {
+            // ---- burst epilogue with masks: map in registers, shuffle row sums, direct stores ----
+            double ni[8], nbv[4][2];
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
-            const int r = wm * 64 + mt * 8 + g;                  // r & 7 == g
+            for (int mt = 0; mt < 8; ++mt) ni[mt] = (KID == 0) ? -p.km.p0 * p.na[i0 + wm * 64 + mt * 8 + g] : 0.0;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-                const int c = wn * 2 + (nt >> 1), u = (nt & 1) * 4 + t;
-                *reinterpret_cast<double2*>(S + stage_off(r, c, u)) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                nbv[nt][0] = nbv[nt][1] = 0.0;
+                if (KID == 0) {
+                    const double2 v = *reinterpret_cast<const double2*>(p.nb + j0 + wn * 32 + nt * 8 + 2 * t);
+                    nbv[nt][0] = -p.km.p0 * v.x; nbv[nt][1] = -p.km.p0 * v.y;   // pre-scaled by -gamma (gram_map)
+                }
             }
+            double* rsb = rs + (fin & 1) * 2 * BM;
+            if (mirror) gram_epilogue_mirror<KID, true>(p, acc, ni, i0, j0, wm, wn, g, t, rsb, Kmir, rpmir, mir_row0, tbuf);
+            else        gram_epilogue_plain<KID, true>(p, acc, ni, nbv, i0, j0, wm, wn, g, t, rsb);
+            if (p.rowpart) {
+                bar_sync_compute();                  // both column halves of every row are in smem
+                p.rowpart[(long)tx * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
+            }
+            ++fin;
+        } else {
+            // ---- park the raw dot products in TMEM; they are mapped during the next tile ----
+            tmem_park(taddr, acc);
+            pk.valid = true; pk.mirror = mirror; pk.i0 = i0; pk.j0 = j0; pk.tx = tx; pk.q = 0;
+            pk.Kmir = Kmir; pk.rpmir = rpmir; pk.mir_row0 = mir_row0; pk.cs0 = pk.cs1 = 0.0;
         }
-        // state of the tile now staged: norms (pre-scaled by -gamma), edge flag
-        pv.valid = true; pv.i0 = i0; pv.j0 = j0; pv.q = 0; pv.rs = pv.rs0 = 0.0;
-        {
-            const long ig0 = (p.diag_shift >= 0) ? i0 + p.diag_shift : -(1L << 40);
-            pv.edge = (i0 + BM > p.rows_valid) || (j0 + BN > p.cols_valid) || (ig0 < j0 + BN && ig0 + BM > j0);
-        }
-        if (KID == 0) {
-            pv.ni0 = -p.km.p0 * p.na[i0 + wm * 64 + lane];
-            pv.ni1 = -p.km.p0 * p.na[i0 + wm * 64 + lane + 32];
-            colw[lane] = -p.km.p0 * p.nb[j0 + wn * 32 + lane];
-        }
-        __syncwarp();                                            // staging block and colw: this warp only
-        ++tcount;
     }
-    // the last tile of this CTA has no successor to hide behind
-    if (pv.valid) {
-        if (pv.edge) map_edge_tile<KID>(p, S, colw, wm, wn, lane, pv);
-        for (; pv.q < UNITS; ++pv.q) map_unit<KID>(p, S, colw, wm, wn, lane, pv, pv.q);
-        FX_GRAM_FINISH_PREV();
+    if (pk.valid) {
+        // the last tile of this CTA has no successor to hide behind
+        for (; pk.q < UNITS; ++pk.q) {
+            if (pk.mirror) parked_unit<KID, true>(p, pk, pk.q, taddr, wm, wn, g, t, lane, racc, tbuf);
+            else           parked_unit<KID, false>(p, pk, pk.q, taddr, wm, wn, g, t, lane, racc, tbuf);
+        }
+        parked_finish(p, pk, wm, wn, g, t, lane, tid, racc, rs + (fin & 1) * 2 * BM);
     }
-#undef FX_GRAM_FINISH_PREV
 #undef FX_GRAM_KSTEP
 #undef FX_GRAM_KSTEP_END
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // mirrored tiles have left the SM
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    bar_sync_compute();                                          // every MMA warp is done with its TMEM quarter
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(*tmem_base));
 }
 
 // ---- naive cross-check variant: one thread per output element -------------------------------
@@ -460,28 +606,24 @@ bool use_v3() {
 }
 
 template <int KID, int UPS>
-int launch_ws2(fx_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmK,
-               const GramParams& p, unsigned grid) {
-    FX_SET_SMEM_ONCE(ctx, (gram_ws_kernel<KID, UPS>), SMEM_BYTES);
-    gram_ws_kernel<KID, UPS><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmK, p);
+int launch_k2(fx_ctx* ctx, const GramParams& p, unsigned grid) {
+    FX_SET_SMEM_ONCE(ctx, (gram_dmma_kernel<KID, UPS>), SMEM_BYTES);
+    gram_dmma_kernel<KID, UPS><<<grid, 256, SMEM_BYTES, ctx->stream>>>(p);
     return 0;
 }
 template <int KID>
-int launch_ws(fx_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmK,
-              const GramParams& p, unsigned grid) {
-    // units mapped per k-step: the map of the previous tile should be done after about half of the
-    // k-steps, so that the store warps have the other half to send it out
+int launch_k(fx_ctx* ctx, const GramParams& p, unsigned grid) {
     const int kt = p.kt;
-    if (kt >= 64) return launch_ws2<KID, 1>(ctx, tmA, tmB, tmK, p, grid);
-    if (kt >= 32) return launch_ws2<KID, 2>(ctx, tmA, tmB, tmK, p, grid);
-    if (kt >= 16) return launch_ws2<KID, 4>(ctx, tmA, tmB, tmK, p, grid);
-    return launch_ws2<KID, 8>(ctx, tmA, tmB, tmK, p, grid);
+    if (kt >= 32) return launch_k2<KID, 1>(ctx, p, grid);
+    if (kt >= 16) return launch_k2<KID, 2>(ctx, p, grid);
+    if (kt >= 8) return launch_k2<KID, 4>(ctx, p, grid);
+    return launch_k2<KID, 8>(ctx, p, grid);
 }
 
 }  // namespace
 
-// Number of per-tile row-sum partials (slots of `rowpart`) the Gram kernel writes per row.
-int64_t fx_gram_rowpart_slots(int64_t ldk) { return ldk / 64; }
+// slots of GramArgs::rowpart per row: one partial row sum per 64-column output tile
+int64_t fx_gram_rowpart_slots(int64_t ldk) { return ldk / BN; }
 
 int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, int64_t d_pad,
                        double* norms) {
@@ -494,7 +636,7 @@ int fx_launch_rownorms(fx_ctx* ctx, const double* P, int64_t ld, int64_t nobs, i
 
 int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     if (use_v3()) return fx_launch_gram_v3(ctx, a, variant);
-    if (a.rows_pad % BM || a.ldk % BN || a.d_pad % 16 || a.lda % 2 || a.ldb % 2) {
+    if (a.rows_pad % BM || a.ldk % BN || a.d_pad % BK || a.lda % 2 || a.ldb % 2) {
         fx_set_error("gram: bad padding rows_pad=%lld ldk=%lld d_pad=%lld", (long long)a.rows_pad,
                      (long long)a.ldk, (long long)a.d_pad);
         return FX_ERR_CUDA;
@@ -530,46 +672,16 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     }
     if (a.rows_pad == 0 || a.ldk == 0) return 0;
     if (variant == 0) {
-        PFN_encodeTiled enc = get_encode();
-        if (!enc) {
-            fx_set_error("gram: cuTensorMapEncodeTiled is not available from this driver");
-            return FX_ERR_CUDA;
-        }
-        CUtensorMap tmA, tmB, tmK;
-        auto operand_map = [&](CUtensorMap* tm, const double* ptr, int64_t nobs, int64_t ld) -> int {
-            // feature-major operand: dim0 = observations (contiguous), dim1 = features
-            cuuint64_t dims[2] = {(cuuint64_t)nobs, (cuuint64_t)a.d_pad};
-            cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-            cuuint32_t box[2] = {PITCH, BK};
-            cuuint32_t es[2] = {1, 1};
-            CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ptr, dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) { fx_set_error("gram: operand tensor map rejected (CUresult %d)", (int)r); return FX_ERR_CUDA; }
-            return 0;
-        };
-        FX_TRY(operand_map(&tmA, a.A, a.rows_pad, a.lda));
-        FX_TRY(operand_map(&tmB, a.B, a.ldk, a.ldb));
-        {
-            cuuint64_t dims[3] = {16, (cuuint64_t)a.rows_pad, (cuuint64_t)(a.ldk / 16)};
-            cuuint64_t strides[2] = {(cuuint64_t)a.ldk * 8, 128};
-            cuuint32_t box[3] = {16, BM, BN / 16};
-            cuuint32_t es[3] = {1, 1, 1};
-            CUresult r = enc(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)a.K, dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) { fx_set_error("gram: tensor map for K rejected (CUresult %d)", (int)r); return FX_ERR_CUDA; }
-        }
-        const long want = ctx->sm_count > 0 ? ctx->sm_count : 148;
+        long want = 2L * (ctx->sm_count > 0 ? ctx->sm_count : 148);
         const unsigned grid = (unsigned)(p.tiles_total < want ? p.tiles_total : want);
         switch (kernel_variant(p.km.id, p.km.ipow)) {
-            case 0: FX_TRY(launch_ws<0>(ctx, tmA, tmB, tmK, p, grid)); break;
-            case 1: FX_TRY(launch_ws<1>(ctx, tmA, tmB, tmK, p, grid)); break;
-            case 2: FX_TRY(launch_ws<2>(ctx, tmA, tmB, tmK, p, grid)); break;
-            case 3: FX_TRY(launch_ws<3>(ctx, tmA, tmB, tmK, p, grid)); break;
-            case 4: FX_TRY(launch_ws<4>(ctx, tmA, tmB, tmK, p, grid)); break;
-            case 5: FX_TRY(launch_ws<5>(ctx, tmA, tmB, tmK, p, grid)); break;
-            default: FX_TRY(launch_ws<6>(ctx, tmA, tmB, tmK, p, grid)); break;
+            case 0: FX_TRY(launch_k<0>(ctx, p, grid)); break;
+            case 1: FX_TRY(launch_k<1>(ctx, p, grid)); break;
+            case 2: FX_TRY(launch_k<2>(ctx, p, grid)); break;
+            case 3: FX_TRY(launch_k<3>(ctx, p, grid)); break;
+            case 4: FX_TRY(launch_k<4>(ctx, p, grid)); break;
+            case 5: FX_TRY(launch_k<5>(ctx, p, grid)); break;
+            default: FX_TRY(launch_k<6>(ctx, p, grid)); break;
         }
         ctx->launches++;
     } else {

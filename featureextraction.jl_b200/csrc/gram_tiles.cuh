@@ -2,10 +2,9 @@
 // of __host__ __device__ templates so that the very same code is exercised on the CPU
 // (tests/host/gram_tiles_host.cu, driven by tests/test_device_math_host.py).  P is any struct
 // with the fields tiles_x, tiles_y, sym, rank, world, diag_shift (GramParams in gram.cu).
-// Output tiles are SQUARE (128 x 128), so the mirror image of a tile is again one tile.
 #pragma once
 
-constexpr int FX_GRAM_BM = 128, FX_GRAM_BN = 128;
+constexpr int FX_GRAM_BM = 128, FX_GRAM_BN = 64;
 
 // What this rank does with tile (ty, tx): 0 = skip (someone's mirror store produces it),
 // 1 = compute, 2 = compute and mirror into block `peer` (== own block inside the diagonal block).
@@ -14,31 +13,30 @@ __host__ __device__ __forceinline__ int tile_role(const P& p, int ty, int tx, in
     constexpr int BN = FX_GRAM_BN;
     peer = p.rank;
     if (!p.sym) return 1;
-    const int bw = p.tiles_y;                                     // tile-columns per rank block
-    const int dblk = (int)(p.diag_shift / BN);
-    const int c = (p.sym == 2) ? tx / bw : ((tx >= dblk && tx < dblk + bw) ? p.rank : -1);
+    const int bw = 2 * p.tiles_y;                                 // tile-columns per rank block
+    const int c = (p.sym == 2) ? tx / bw : ((tx >= (int)(p.diag_shift / BN) && tx < (int)(p.diag_shift / BN) + bw) ? p.rank : -1);
     if (c == p.rank) {
-        const int rel = tx - dblk;
-        if (rel < ty) return 0;                                   // left of the diagonal
-        return rel > ty ? 2 : 1;
+        const int rel = tx - (int)(p.diag_shift / BN);
+        if (rel < 2 * ty) return 0;                               // left of the diagonal
+        return rel >= 2 * ty + 2 ? 2 : 1;
     }
     if (p.sym != 2) return 1;
     const int delta = (c - p.rank + p.world) % p.world;
     bool own;
     if (2 * delta < p.world) own = true;
     else if (2 * delta > p.world) own = false;
-    else own = (((ty + (tx - c * bw)) & 1) == (p.rank < c ? 0 : 1));      // opposite blocks: checkerboard
+    else own = (((ty + (tx - c * bw) / 2) & 1) == (p.rank < c ? 0 : 1));   // opposite blocks: checkerboard
     peer = c;
     return own ? 2 : 0;
 }
 
 // Tile order: column panels of PANEL tile-columns swept over all row blocks, so that the panel's
-// slab of the column operand (PANEL x 262 KB at d=256) stays L2-resident while the row operand
+// slab of the column operand (PANEL x 131 KB at d=256) stays L2-resident while the row operand
 // streams; a plain row-major sweep re-reads all of X from HBM once per row block.
 // sym == 2: the sweep goes rank block by rank block and starts at the rank's OWN block
 // (c = rank, rank+1, ... mod world), so that at any moment the ranks mirror into pairwise distinct
 // peers (a permutation over NVSwitch) instead of all into the same one.
-constexpr int FX_GRAM_PANEL = 64;
+constexpr int FX_GRAM_PANEL = 128;
 template <class P>
 __host__ __device__ __forceinline__ void tile_coords(const P& p, long tile, long& i0, long& j0, int& tx) {
     constexpr int PANEL = FX_GRAM_PANEL;

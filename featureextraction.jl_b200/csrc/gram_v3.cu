@@ -24,7 +24,7 @@
 // STRAIGHT INTO THE PEER'S K over NVLink (plain st.global to the IPC-mapped address), so every
 // rank executes ~half of its row block and no separate exchange step exists.
 #include "fx_kernels.cuh"
-#include "gram_tiles_v3.cuh"
+#include "gram_tiles.cuh"
 
 namespace {
 

@@ -40,7 +40,7 @@ class GlooOps:
 
 def peer_symmetric_gram(kern, X, n, world, rank):
     """The cross-rank symmetric Gram of csrc/gram.cu (sym = 2) with the peer stores emulated by an
-    all-reduce: every rank computes only the 128x128 tiles sharding.gram_tile_roles gives it and
+    all-reduce: every rank computes only the 128x64 tiles sharding.gram_tile_roles gives it and
     'stores' each mirrored tile transposed into the owning rank's rows; the column sums of a
     mirrored tile are the owner's row-sum partials.  Returns this rank's padded row block
     [ld][n_ld] and its row sums [ld]; asserts every element was written exactly once."""
@@ -55,15 +55,15 @@ def peer_symmetric_gram(kern, X, n, world, rank):
         for tx in range(role.shape[1]):
             if role[ty, tx] == 0:
                 continue
-            gi, gj = r0 + 128 * ty, 128 * tx
-            tile = O.kernelmatrix(kern, Xp[gi:gi + 128], Xp[gj:gj + 128])
-            tile = tile * valid[gi:gi + 128, None] * valid[None, gj:gj + 128]     # padding written as 0
-            writes[gi:gi + 128, gj:gj + 128] += tile; count[gi:gi + 128, gj:gj + 128] += 1
+            gi, gj = r0 + 128 * ty, 64 * tx
+            tile = O.kernelmatrix(kern, Xp[gi:gi + 128], Xp[gj:gj + 64])
+            tile = tile * valid[gi:gi + 128, None] * valid[None, gj:gj + 64]     # padding written as 0
+            writes[gi:gi + 128, gj:gj + 64] += tile; count[gi:gi + 128, gj:gj + 64] += 1
             rsum[gi:gi + 128] += tile.sum(axis=1)
             if role[ty, tx] == 2:
                 assert gj // ld == target[ty, tx]
-                writes[gj:gj + 128, gi:gi + 128] += tile.T; count[gj:gj + 128, gi:gi + 128] += 1
-                rsum[gj:gj + 128] += tile.sum(axis=0)
+                writes[gj:gj + 64, gi:gi + 128] += tile.T; count[gj:gj + 64, gi:gi + 128] += 1
+                rsum[gj:gj + 64] += tile.sum(axis=0)
     for a in (writes, count, rsum):
         t = torch.from_numpy(a)
         dist.all_reduce(t)

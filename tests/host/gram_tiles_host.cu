@@ -1,7 +1,7 @@
 // Host harness for the Gram kernel's tile ownership and sweep order: includes the very header the
 // kernel uses (csrc/gram_tiles.cuh, __host__ __device__ templates) and checks, for every rank of a
 // world, that (1) tile_coords is a bijection of the tile index onto the tile grid, (2) over all ranks
-// every 128x128 tile of the global matrix is produced exactly once (computed, or mirrored by exactly
+// every 64x64 cell of the global matrix is produced exactly once (computed, or mirrored by exactly
 // one tile), (3) in sym = 2 the k-th block of every rank's sweep targets pairwise distinct peers.
 // Prints one line per (world, rank) with a checksum that tests/test_device_math_host.py compares
 // with the Python restatement (sharding.gram_tile_roles).  Test infrastructure, not product.
@@ -22,8 +22,8 @@ int main(int argc, char** argv) {
     int failures = 0;
     for (int sym = 1; sym <= 2; ++sym)
         for (int world = 1; world <= 8; ++world) {
-            const int bw = tiles_y, tx_n = bw * world;
-            std::vector<int> cells((size_t)tx_n * tx_n, 0);          // 128x128 tiles of the global matrix
+            const int bw = 2 * tiles_y, tx_n = bw * world;
+            std::vector<int> cells((size_t)tx_n * tx_n, 0);          // 64x64 cells of the global matrix
             std::vector<int> first_target((size_t)world * world, -1);
             for (int rank = 0; rank < world; ++rank) {
                 P p{tx_n, tiles_y, sym, rank, world, (long)rank * tiles_y * FX_GRAM_BM};
@@ -41,12 +41,12 @@ int main(int argc, char** argv) {
                     checksum += (long)role * (ty * 131 + tx * 7 + 1) + (role == 2 ? 1000003L * peer : 0);
                     if (role == 0) continue;
                     ++executed;
-                    const int gi = rank * tiles_y + ty;
-                    cells[(size_t)gi * tx_n + tx]++;
+                    const int gi = 2 * (rank * tiles_y + ty);
+                    cells[(size_t)gi * tx_n + tx]++; cells[(size_t)(gi + 1) * tx_n + tx]++;
                     if (role == 2) {
                         if (sym == 1 && peer != rank) ++failures;
                         if (tx / bw != peer) ++failures;                 // mirrored tile lands in the block it came from
-                        cells[(size_t)tx * tx_n + gi]++;
+                        cells[(size_t)tx * tx_n + gi]++; cells[(size_t)tx * tx_n + gi + 1]++;
                         // block order index of this tile in the rank's sweep
                         const int kb = (int)(t / ((long)bw * tiles_y));
                         if (sym == 2 && peer != rank) {

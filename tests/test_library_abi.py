@@ -75,24 +75,24 @@ def test_sharding_rules():
 @pytest.mark.parametrize("peer", [False, True])
 def test_symmetric_gram_tile_ownership_covers_every_tile_once(world, peer):
     """The ownership rule of the symmetric Gram kernel (csrc/gram.cu tile_role, restated in
-    sharding.gram_tile_roles): over all ranks every 128x128 tile of the global matrix is produced
+    sharding.gram_tile_roles): over all ranks every 64x64 cell of the global matrix is produced
     exactly once, either by the tile that computes it or by exactly one mirror store."""
     import numpy as np
     n = 128 * 3 * world - 5
     ld = fxb200.sharding.row_partition(n, world)[0]
     ty_n = ld // 128
-    cells = np.zeros((ty_n * world, ty_n * world), dtype=np.int64)           # 128x128 tiles
+    cells = np.zeros((2 * ty_n * world, 2 * ty_n * world), dtype=np.int64)   # 64x64 cells
     for r in range(world):
         role, target = fxb200.sharding.gram_tile_roles(n, world, r, peer)
         for ty in range(role.shape[0]):
             for tx in range(role.shape[1]):
                 if role[ty, tx] == 0:
                     continue
-                gi = r * ty_n + ty
-                cells[gi, tx] += 1
-                if role[ty, tx] == 2:                        # the transposed tile
+                gi = 2 * (r * ty_n + ty)                     # first 64-row cell of the 128-row tile
+                cells[gi:gi + 2, tx] += 1
+                if role[ty, tx] == 2:                        # transposed: 64 rows x 128 columns
                     assert peer or target[ty, tx] == r
-                    cells[tx, gi] += 1
+                    cells[tx, gi:gi + 2] += 1
     assert (cells == 1).all()
     ex = [fxb200.sharding.gram_tiles_executed(n, world, r, peer)[0] for r in range(world)]
     assert max(ex) - min(ex) <= ty_n                      # balanced across ranks
@@ -218,20 +218,20 @@ def test_sharding_properties_hypothesis():
         qp = query_partition(m, world)
         assert sum(c for _, c in qp) == m and all(qp[i][0] + qp[i][1] == qp[i + 1][0] for i in range(world - 1))
         ty_n = ld // 128
-        cells = np.zeros((ty_n * world, ty_n * world), dtype=np.int64)
+        cells = np.zeros((2 * ty_n * world, 2 * ty_n * world), dtype=np.int64)
         ex = []
         for r in range(world):
             role, target = gram_tile_roles(n, world, r, peer=True)
             ex.append(int((role > 0).sum()))
             tys, txs = np.nonzero(role)
             for ty, tx in zip(tys, txs):
-                gi = r * ty_n + ty
-                cells[gi, tx] += 1
+                gi = 2 * (r * ty_n + ty)
+                cells[gi:gi + 2, tx] += 1
                 if role[ty, tx] == 2:
-                    assert tx // ty_n == target[ty, tx]
-                    cells[tx, gi] += 1
+                    assert tx // (2 * ty_n) == target[ty, tx]
+                    cells[tx, gi:gi + 2] += 1
         assert (cells == 1).all()
-        assert max(ex) - min(ex) <= max(1, ty_n)      # an odd checkerboard leaves one tile over
+        assert max(ex) - min(ex) <= max(2, ty_n)      # an odd checkerboard leaves one super-tile (2 tiles) over
 
     prop()
 
