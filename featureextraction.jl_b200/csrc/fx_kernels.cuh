@@ -183,3 +183,9 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
 int fx_model_build(fx_ctx* ctx, const GramStage& g, int kernel_id, const double* kp, int k, const double* W,
                    bool centered, bool is_klda, fx_model** out);
 int fx_launch_indicator(fx_ctx* ctx, const int* ydev, int64_t n, int64_t ldr, int cp, double* E);
+
+// ---- linear.cu: device core of lda! (shared with the dense path of fx_klda_fit_f64) ---------------
+size_t fx_lda_core_bytes(fx_ctx* ctx, int64_t n, int64_t p);
+int fx_lda_core(fx_ctx* ctx, double* Xd, int64_t n, int64_t p, int64_t ld, const int64_t* y, int k,
+                const double* freq, const double* inv_cnt, double alpha_b, double eps_b, double alpha_w,
+                double eps_w, double** Vd_out, int64_t* ldv_out, double** lam_out, int hinfo[8]);

@@ -50,12 +50,12 @@ constexpr int STAGE_D = BK * AS + BK * BS;      // doubles per stage (3200 -> 25
 // 8-byte stores for lanes (g,t) -> word (2t+q)*TS + g) -- sent off with 512-byte bulk stores
 constexpr int TS = 66, TBUF_D = 8 * TS;
 constexpr int UNITS = 32;                       // (mt, nt) accumulator pairs per lane per tile
-// smem (doubles): stages | rs [2 bufs][2 halves][BM] | 16 (barriers + TMEM base) | tstage | rowacc [4 warps][8][32]
+// smem (doubles): stages | rs [2 bufs][2 halves][BM] | 16 (barriers + TMEM base) | tstage
+// (114,816 bytes: two CTAs per SM exactly fit the 228 KB of an SM)
 constexpr int OFF_RS = STAGES * STAGE_D;
 constexpr int OFF_BAR = OFF_RS + 4 * BM;
 constexpr int OFF_TST = OFF_BAR + 16;
-constexpr int OFF_RACC = OFF_TST + 4 * 2 * TBUF_D;
-constexpr int SMEM_BYTES = (OFF_RACC + 4 * 8 * 32) * 8;
+constexpr int SMEM_BYTES = (OFF_TST + 4 * 2 * TBUF_D) * 8;
 
 // 1-D bulk store shared -> global (TMA engine); the destination may be a peer GPU's memory
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
@@ -149,7 +149,7 @@ struct Parked {
 // Interior tiles only: no masks, no same-point test.
 template <int KID, bool MIRROR>
 __device__ __forceinline__ void parked_unit(const GramParams& p, Parked& pk, int q, uint32_t taddr, int wm, int wn, int g,
-                                            int t, int lane, double* racc, double* tbuf) {
+                                            int t, int lane, double* rsb, double* tbuf) {
     const int mt = q & 7, nt = q >> 3;
     const double2 raw = tmem_fetch2(taddr + 4 * (4 * mt + nt));
     const long i = pk.i0 + wm * 64 + mt * 8 + g;
@@ -163,7 +163,14 @@ __device__ __forceinline__ void parked_unit(const GramParams& p, Parked& pk, int
     const double v0 = gram_map<KID>(p.km, raw.x, ni, nb0, false);
     const double v1 = gram_map<KID>(p.km, raw.y, ni, nb1, false);
     *reinterpret_cast<double2*>(p.K + i * p.ldk + jb) = make_double2(v0, v1);
-    racc[mt * 32 + lane] += v0 + v1;                            // this lane's private slot
+    if (p.rowpart) {
+        // row-sum slot of (column half wn, row): folded over the four t lanes, then accumulated by the
+        // t == 0 lane alone, in unit order -- deterministic (no atomics)
+        double rsum = v0 + v1;
+        rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
+        rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
+        if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] += rsum;
+    }
     if (MIRROR) {
         double* tb = tbuf + (nt & 1) * TBUF_D;
         if (mt == 0 && nt >= 2) {
@@ -205,25 +212,18 @@ __device__ __forceinline__ void parked_unit(const GramParams& p, Parked& pk, int
     }
 }
 
-// All units of the parked tile are done: drain the mirror stores, fold the per-lane row-sum slots
-// (over the four t lanes), and -- after the 4 MMA warps met -- write the tile's row-sum partials.
-__device__ __forceinline__ void parked_finish(const GramParams& p, Parked& pk, int wm, int wn, int g, int t, int lane,
-                                              int tid, double* racc, double* rsb) {
+// All units of the parked tile are done: drain the mirror stores and -- after the 4 MMA warps met --
+// write the tile's row-sum partials (and clear the slots for the tile after the next).
+__device__ __forceinline__ void parked_finish(const GramParams& p, Parked& pk, int lane, int tid, double* rsb) {
     if (pk.mirror) {
         if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
     }
-#pragma unroll
-    for (int mt = 0; mt < 8; ++mt) {
-        double v = racc[mt * 32 + lane];
-        racc[mt * 32 + lane] = 0.0;
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = v;
-    }
     if (p.rowpart) {
         bar_sync_compute();                  // both column halves of every row are in smem
         p.rowpart[(long)pk.tx * p.rows_pad + pk.i0 + tid] = rsb[tid] + rsb[BM + tid];
+        rsb[tid] = 0.0;                      // this buffer is used again by the tile after the next
+        rsb[BM + tid] = 0.0;
     }
     pk.valid = false;
 }
@@ -374,7 +374,6 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     uint64_t* empty = full + STAGES;
     uint32_t* tmem_base = reinterpret_cast<uint32_t*>(empty + STAGES);
     double* tstage = smem + OFF_TST;
-    double* racc_all = smem + OFF_RACC;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -390,7 +389,7 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < 4 * 8 * 32; i += 256) racc_all[i] = 0.0;
+    for (int i = tid; i < 4 * BM; i += 256) rs[i] = 0.0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -426,7 +425,6 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int wm = warp >> 1, wn = warp & 1;
     const uint32_t taddr = *tmem_base + ((uint32_t)(32 * warp) << 16);      // this warp's TMEM lane quarter
-    double* racc = racc_all + warp * (8 * 32);
     double* tbuf = tstage + warp * 2 * TBUF_D;
     Parked pk;
     pk.valid = false; pk.mirror = false; pk.q = UNITS; pk.i0 = pk.j0 = 0; pk.tx = 0;
@@ -479,7 +477,7 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
                 for (; kt < KT && pk.q < UNITS; ++kt) {
                     FX_GRAM_KSTEP();
 #pragma unroll
-                    for (int j = 0; j < UPS; ++j) parked_unit<KID, true>(p, pk, pk.q + j, taddr, wm, wn, g, t, lane, racc, tbuf);
+                    for (int j = 0; j < UPS; ++j) parked_unit<KID, true>(p, pk, pk.q + j, taddr, wm, wn, g, t, lane, rs + (fin & 1) * 2 * BM, tbuf);
                     pk.q += UPS;
                     ++it;
                     FX_GRAM_KSTEP_END();
@@ -488,7 +486,7 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
                 for (; kt < KT && pk.q < UNITS; ++kt) {
                     FX_GRAM_KSTEP();
 #pragma unroll
-                    for (int j = 0; j < UPS; ++j) parked_unit<KID, false>(p, pk, pk.q + j, taddr, wm, wn, g, t, lane, racc, tbuf);
+                    for (int j = 0; j < UPS; ++j) parked_unit<KID, false>(p, pk, pk.q + j, taddr, wm, wn, g, t, lane, rs + (fin & 1) * 2 * BM, tbuf);
                     pk.q += UPS;
                     ++it;
                     FX_GRAM_KSTEP_END();
@@ -503,10 +501,10 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
         if (pk.valid) {
             // fewer k-steps than the parked tile needed (small d): the rest in one go
             for (; pk.q < UNITS; ++pk.q) {
-                if (pk.mirror) parked_unit<KID, true>(p, pk, pk.q, taddr, wm, wn, g, t, lane, racc, tbuf);
-                else           parked_unit<KID, false>(p, pk, pk.q, taddr, wm, wn, g, t, lane, racc, tbuf);
+                if (pk.mirror) parked_unit<KID, true>(p, pk, pk.q, taddr, wm, wn, g, t, lane, rs + (fin & 1) * 2 * BM, tbuf);
+                else           parked_unit<KID, false>(p, pk, pk.q, taddr, wm, wn, g, t, lane, rs + (fin & 1) * 2 * BM, tbuf);
             }
-            parked_finish(p, pk, wm, wn, g, t, lane, tid, racc, rs + (fin & 1) * 2 * BM);
+            parked_finish(p, pk, lane, tid, rs + (fin & 1) * 2 * BM);
             ++fin;
         }
 
@@ -538,6 +536,8 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
             if (p.rowpart) {
                 bar_sync_compute();                  // both column halves of every row are in smem
                 p.rowpart[(long)tx * p.rows_pad + i0 + tid] = rsb[tid] + rsb[BM + tid];
+                rsb[tid] = 0.0;                      // parked tiles ACCUMULATE into these slots
+                rsb[BM + tid] = 0.0;
             }
             ++fin;
         } else {
@@ -550,10 +550,10 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
     if (pk.valid) {
         // the last tile of this CTA has no successor to hide behind
         for (; pk.q < UNITS; ++pk.q) {
-            if (pk.mirror) parked_unit<KID, true>(p, pk, pk.q, taddr, wm, wn, g, t, lane, racc, tbuf);
-            else           parked_unit<KID, false>(p, pk, pk.q, taddr, wm, wn, g, t, lane, racc, tbuf);
+            if (pk.mirror) parked_unit<KID, true>(p, pk, pk.q, taddr, wm, wn, g, t, lane, rs + (fin & 1) * 2 * BM, tbuf);
+            else           parked_unit<KID, false>(p, pk, pk.q, taddr, wm, wn, g, t, lane, rs + (fin & 1) * 2 * BM, tbuf);
         }
-        parked_finish(p, pk, wm, wn, g, t, lane, tid, racc, rs + (fin & 1) * 2 * BM);
+        parked_finish(p, pk, lane, tid, rs + (fin & 1) * 2 * BM);
     }
 #undef FX_GRAM_KSTEP
 #undef FX_GRAM_KSTEP_END

@@ -215,6 +215,101 @@ extern "C" int fx_project_f64(fx_ctx* ctx, const double* W, int64_t p, int k, in
     return 0;
 }
 
+// Device core of lda! (klda.jl:34-61) on a data matrix that already sits in HBM: Xd is ld x pp
+// column-major (pp = roundup(p, 8) columns, zero padded; DESTROYED: it becomes H_w).  Used by fx_lda_f64
+// and by the dense path of fx_klda_fit_f64, where the data matrix is the kernel matrix itself
+// (SURVEY.md A.3).  Buffers come from the arena (fx_lda_core_bytes).  Leaves the p x p generalized
+// eigenvectors (leading dimension *ldv_out, V' Sigma_w' V = I, descending) and eigenvalues on the
+// device; hinfo[1], hinfo[3] = Jacobi convergence flags, hinfo[4] = Sigma_w' not positive definite.
+size_t fx_lda_core_bytes(fx_ctx* ctx, int64_t n, int64_t p) {
+    const int64_t ld = round_up(n, 128), pp = round_up(p, 8), ldy = round_up(pp, 128);
+    size_t s = fx_ts_tn_scratch(ctx, (int)pp, (int)pp, ld);
+    size_t s2 = fx_ts_tn_scratch(ctx, 64, (int)pp, ld);
+    if (s2 > s) s = s2;
+    size_t s3 = fx_ts_tn_scratch(ctx, (int)pp, (int)pp, ldy);
+    if (s3 > s) s = s3;
+    return fx_align256(s * 8) + fx_align256((size_t)64 * ld * 8) + 10 * fx_align256((size_t)pp * ldy * 8) +
+           fx_align256((size_t)ld * 4) + 65536;
+}
+
+int fx_lda_core(fx_ctx* ctx, double* Xd, int64_t n, int64_t p, int64_t ld, const int64_t* y, int k,
+                const double* freq, const double* inv_cnt, double alpha_b, double eps_b, double alpha_w,
+                double eps_w, double** Vd_out, int64_t* ldv_out, double** lam_out, int hinfo[8]) {
+    cudaStream_t s = ctx->stream;
+    const int pp = (int)round_up(p, 8), kp = (int)round_up(k, 8);
+    const int64_t ldy = round_up(pp, 128);                     // p x p operands padded to 128 rows for tsgemm
+    auto dalloc = [&](size_t d) { return (double*)fx_arena_alloc(ctx, d * 8); };
+    size_t scr_doubles = fx_ts_tn_scratch(ctx, pp, pp, ld);
+    {
+        size_t s2 = fx_ts_tn_scratch(ctx, 64, pp, ld), s3 = fx_ts_tn_scratch(ctx, pp, pp, ldy);
+        if (s2 > scr_doubles) scr_doubles = s2;
+        if (s3 > scr_doubles) scr_doubles = s3;
+    }
+    double* scr = dalloc(scr_doubles);
+    double* E = dalloc((size_t)kp * ld);
+    double* sums = dalloc((size_t)kp * pp); double* means = dalloc((size_t)kp * pp); double* mu = dalloc(pp);
+    const int64_t ldh = 128;                                   // H_b stored as (128 rows x pp), rows >= k zero
+    double* Hb = dalloc((size_t)pp * ldh);
+    double* Sb = dalloc((size_t)pp * pp); double* Sw = dalloc((size_t)pp * pp);
+    double* U = dalloc((size_t)pp * pp); double* Uw = dalloc((size_t)pp * pp); double* dvals = dalloc(pp + 8);
+    double* Y = dalloc((size_t)pp * ldy); double* T = dalloc((size_t)pp * ldy); double* SbP = dalloc((size_t)pp * ldy);
+    double* Mm = dalloc((size_t)pp * pp); double* Zv = dalloc((size_t)pp * pp); double* lam = dalloc(pp + 8);
+    double* Vd = dalloc((size_t)pp * ldy);
+    double* dfreq = dalloc(64); double* dinv = dalloc(64);
+    int* ydev = (int*)fx_arena_alloc(ctx, (size_t)ld * 4);
+    int* info = (int*)fx_arena_alloc(ctx, 64);
+    if (!info || !Vd || !scr) { fx_set_error("internal: arena too small for the LDA core"); return FX_ERR_OOM; }
+    {
+        std::vector<int> y32(ld, 0);
+        for (int64_t i = 0; i < n; ++i) y32[i] = (int)y[i];
+        FX_CUDA(cudaMemcpyAsync(ydev, y32.data(), (size_t)ld * 4, cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaMemcpyAsync(dfreq, freq, k * 8, cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaMemcpyAsync(dinv, inv_cnt, k * 8, cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaStreamSynchronize(s));
+    }
+    FX_TRY(fx_launch_indicator(ctx, ydev, n, ld, kp, E));
+    // class sums -> means, mu, H_b (klda.jl:47-53)
+    FX_TRY(fx_launch_ts_tn(ctx, E, kp, Xd, pp, ld, ld, sums, kp, scr, scr_doubles, 0));
+    FX_CUDA(cudaMemsetAsync(Hb, 0, (size_t)pp * ldh * 8, s));
+    lda_tables_kernel<<<1, 256, 0, s>>>(sums, kp, k, (int)p, pp, dinv, dfreq, means, Hb, ldh, mu);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    // H_w = (X - M[y]) / (n - k)  (klda.jl:49-50):  X -= E * means, then scale
+    FX_TRY(fx_launch_ts_nn(ctx, E, kp, means, kp, pp, -1.0, 1.0, Xd, ld, ld, 0));
+    FX_TRY(fx_launch_vec_axpy(ctx, (int64_t)pp * ld, 1.0 / (double)(n - k) - 1.0, Xd, Xd));
+    // Sigma_b = H_b'H_b, Sigma_w = H_w'H_w (klda.jl:35,39) with shrink / perturb (klda.jl:36-41)
+    FX_TRY(fx_launch_ts_tn(ctx, Hb, pp, Hb, pp, ldh, ldh, Sb, pp, scr, scr_doubles, 0));
+    FX_TRY(fx_launch_ts_tn(ctx, Xd, pp, Xd, pp, ld, ld, Sw, pp, scr, scr_doubles, 0));
+    symmetrize_full_kernel<<<8, 256, 0, s>>>(Sb, pp, (int)p);          // syml! (klda.jl:35,39)
+    symmetrize_full_kernel<<<8, 256, 0, s>>>(Sw, pp, (int)p);
+    regularize_kernel<<<1, 1024, 0, s>>>(Sb, pp, (int)p, alpha_b, eps_b, nullptr);
+    regularize_kernel<<<1, 1024, 0, s>>>(Sw, pp, (int)p, alpha_w, eps_w, nullptr);
+    ctx->launches += 4;
+    FX_LAUNCH_CHECK();
+    // generalized symmetric eigenproblem (common.jl:168-174): Sigma_w = U D U'
+    FX_CUDA(cudaMemsetAsync(SbP, 0, (size_t)pp * ldy * 8, s));
+    FX_CUDA(cudaMemcpy2DAsync(SbP, ldy * 8, Sb, (size_t)pp * 8, p * 8, p, cudaMemcpyDeviceToDevice, s));
+    FX_TRY(fx_launch_jacobi(ctx, Sw, pp, (int)p, U, pp, dvals, Uw, info));
+    FX_CUDA(cudaMemsetAsync(Y, 0, (size_t)pp * ldy * 8, s));
+    scale_cols_kernel<<<1, 1024, 0, s>>>(U, pp, dvals, (int)p, Y, ldy, info + 4);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    // M = Y' Sigma_b Y
+    FX_CUDA(cudaMemsetAsync(T, 0, (size_t)pp * ldy * 8, s));
+    FX_TRY(fx_launch_ts_nn(ctx, SbP, pp, Y, (int)ldy, pp, 1.0, 0.0, T, ldy, ldy, 0));
+    FX_TRY(fx_launch_ts_tn(ctx, Y, pp, T, pp, ldy, ldy, Mm, pp, scr, scr_doubles, 0));
+    symmetrize_full_kernel<<<8, 256, 0, s>>>(Mm, pp, (int)p);
+    ctx->launches++;
+    FX_TRY(fx_launch_jacobi(ctx, Mm, pp, (int)p, Zv, pp, lam, Uw, info + 2));
+    // V = Y Z
+    FX_CUDA(cudaMemsetAsync(Vd, 0, (size_t)pp * ldy * 8, s));
+    FX_TRY(fx_launch_ts_nn(ctx, Y, pp, Zv, pp, pp, 1.0, 0.0, Vd, ldy, ldy, 0));
+    FX_CUDA(cudaMemcpyAsync(hinfo, info, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    *Vd_out = Vd; *ldv_out = ldy; *lam_out = lam;
+    return 0;
+}
+
 extern "C" int fx_lda_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, int64_t ldx, const int64_t* y,
                           int nclass, const double* freq, double alpha_b, double eps_b, double alpha_w,
                           double eps_w, double* V, int64_t ldv, double* lambda, fx_stats* stats) {
@@ -251,75 +346,15 @@ extern "C" int fx_lda_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, in
     }
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
-    FX_TRY(fx_arena_reserve(ctx, lin_bytes(ctx, n, p) + fx_align256((size_t)64 * round_up(n, 128) * 8) * 2));
+    FX_TRY(fx_arena_reserve(ctx, lin_bytes(ctx, n, p) + fx_lda_core_bytes(ctx, n, p)));
     fx_arena_reset(ctx);
     cudaStream_t s = ctx->stream;
     Lin L;
     FX_TRY(upload(ctx, X, n, p, ldx, L));
-    const int pp = L.pp, kp = (int)round_up(k, 8);
-    const int64_t ld = L.ld;
-    auto dalloc = [&](size_t d) { return (double*)fx_arena_alloc(ctx, d * 8); };
-    double* E = dalloc((size_t)kp * ld);
-    double* sums = dalloc((size_t)kp * pp); double* means = dalloc((size_t)kp * pp); double* mu = dalloc(pp);
-    const int64_t ldh = 128;                                   // H_b stored as (128 rows x pp), rows >= k zero
-    double* Hb = dalloc((size_t)pp * ldh);
-    double* Sb = dalloc((size_t)pp * pp); double* Sw = dalloc((size_t)pp * pp);
-    double* U = dalloc((size_t)pp * pp); double* Uw = dalloc((size_t)pp * pp); double* dvals = dalloc(pp + 8);
-    const int64_t ldy = round_up(pp, 128);                     // p x p operands padded to 128 rows for tsgemm
-    double* Y = dalloc((size_t)pp * ldy); double* T = dalloc((size_t)pp * ldy); double* SbP = dalloc((size_t)pp * ldy);
-    double* Mm = dalloc((size_t)pp * pp); double* Zv = dalloc((size_t)pp * pp); double* lam = dalloc(pp + 8);
-    double* Vd = dalloc((size_t)pp * ldy);
-    double* dfreq = dalloc(64); double* dinv = dalloc(64);
-    int* ydev = (int*)fx_arena_alloc(ctx, (size_t)ld * 4);
-    int* info = (int*)fx_arena_alloc(ctx, 64);
-    if (!info || !Vd) { fx_set_error("internal: arena too small"); return FX_ERR_OOM; }
-    {
-        std::vector<int> y32(ld, 0);
-        for (int64_t i = 0; i < n; ++i) y32[i] = (int)y[i];
-        FX_CUDA(cudaMemcpyAsync(ydev, y32.data(), (size_t)ld * 4, cudaMemcpyHostToDevice, s));
-        FX_CUDA(cudaMemcpyAsync(dfreq, freq, k * 8, cudaMemcpyHostToDevice, s));
-        FX_CUDA(cudaMemcpyAsync(dinv, inv_cnt.data(), k * 8, cudaMemcpyHostToDevice, s));
-        FX_CUDA(cudaStreamSynchronize(s));
-    }
-    FX_TRY(fx_launch_indicator(ctx, ydev, n, ld, kp, E));
-    // class sums -> means, mu, H_b (klda.jl:47-53)
-    FX_TRY(fx_launch_ts_tn(ctx, E, kp, L.X, pp, ld, ld, sums, kp, L.scr, L.scr_doubles, 0));
-    FX_CUDA(cudaMemsetAsync(Hb, 0, (size_t)pp * ldh * 8, s));
-    lda_tables_kernel<<<1, 256, 0, s>>>(sums, kp, k, (int)p, pp, dinv, dfreq, means, Hb, ldh, mu);
-    ctx->launches++;
-    FX_LAUNCH_CHECK();
-    // H_w = (X - M[y]) / (n - k)  (klda.jl:49-50):  X -= E * means, then scale
-    FX_TRY(fx_launch_ts_nn(ctx, E, kp, means, kp, pp, -1.0, 1.0, L.X, ld, ld, 0));
-    FX_TRY(fx_launch_vec_axpy(ctx, (int64_t)pp * ld, 1.0 / (double)(n - k) - 1.0, L.X, L.X));
-    // Sigma_b = H_b'H_b, Sigma_w = H_w'H_w (klda.jl:35,39) with shrink / perturb (klda.jl:36-41)
-    FX_TRY(fx_launch_ts_tn(ctx, Hb, pp, Hb, pp, ldh, ldh, Sb, pp, L.scr, L.scr_doubles, 0));
-    FX_TRY(fx_launch_ts_tn(ctx, L.X, pp, L.X, pp, ld, ld, Sw, pp, L.scr, L.scr_doubles, 0));
-    symmetrize_full_kernel<<<8, 256, 0, s>>>(Sb, pp, (int)p);          // syml! (klda.jl:35,39)
-    symmetrize_full_kernel<<<8, 256, 0, s>>>(Sw, pp, (int)p);
-    regularize_kernel<<<1, 1024, 0, s>>>(Sb, pp, (int)p, alpha_b, eps_b, nullptr);
-    regularize_kernel<<<1, 1024, 0, s>>>(Sw, pp, (int)p, alpha_w, eps_w, nullptr);
-    ctx->launches += 4;
-    FX_LAUNCH_CHECK();
-    // generalized symmetric eigenproblem (common.jl:168-174): Sigma_w = U D U'
-    FX_CUDA(cudaMemsetAsync(SbP, 0, (size_t)pp * ldy * 8, s));
-    FX_CUDA(cudaMemcpy2DAsync(SbP, ldy * 8, Sb, (size_t)pp * 8, p * 8, p, cudaMemcpyDeviceToDevice, s));
-    FX_TRY(fx_launch_jacobi(ctx, Sw, pp, (int)p, U, pp, dvals, Uw, info));
-    FX_CUDA(cudaMemsetAsync(Y, 0, (size_t)pp * ldy * 8, s));
-    scale_cols_kernel<<<1, 1024, 0, s>>>(U, pp, dvals, (int)p, Y, ldy, info + 4);
-    ctx->launches++;
-    FX_LAUNCH_CHECK();
-    // M = Y' Sigma_b Y
-    FX_CUDA(cudaMemsetAsync(T, 0, (size_t)pp * ldy * 8, s));
-    FX_TRY(fx_launch_ts_nn(ctx, SbP, pp, Y, (int)ldy, pp, 1.0, 0.0, T, ldy, ldy, 0));
-    FX_TRY(fx_launch_ts_tn(ctx, Y, pp, T, pp, ldy, ldy, Mm, pp, L.scr, L.scr_doubles, 0));
-    symmetrize_full_kernel<<<8, 256, 0, s>>>(Mm, pp, (int)p);
-    ctx->launches++;
-    FX_TRY(fx_launch_jacobi(ctx, Mm, pp, (int)p, Zv, pp, lam, Uw, info + 2));
-    // V = Y Z
-    FX_CUDA(cudaMemsetAsync(Vd, 0, (size_t)pp * ldy * 8, s));
-    FX_TRY(fx_launch_ts_nn(ctx, Y, pp, Zv, pp, pp, 1.0, 0.0, Vd, ldy, ldy, 0));
+    double* Vd = nullptr; double* lam = nullptr; int64_t ldy = 0;
     int hinfo[8] = {0};
-    FX_CUDA(cudaMemcpyAsync(hinfo, info, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_TRY(fx_lda_core(ctx, L.X, n, p, L.ld, y, k, freq, inv_cnt.data(), alpha_b, eps_b, alpha_w, eps_w, &Vd, &ldy,
+                       &lam, hinfo));
     FX_CUDA(cudaMemcpy2DAsync(V, ldv * 8, Vd, ldy * 8, p * 8, p, cudaMemcpyDeviceToHost, s));
     FX_CUDA(cudaMemcpyAsync(lambda, lam, p * 8, cudaMemcpyDeviceToHost, s));
     FX_CUDA(cudaStreamSynchronize(s));
