@@ -8,13 +8,14 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfxb200.so")
+# FXB200_LIB_PATH: load an experimental build instead (kernel A/B measurements; tools/probes/)
+LIB_PATH = os.environ.get("FXB200_LIB_PATH") or os.path.join(_HERE, "csrc", "libfxb200.so")
 
 
 class SolverOpts(C.Structure):
     _fields_ = [("block", C.c_int32), ("max_blocks", C.c_int32), ("max_steps", C.c_int32),
                 ("variant", C.c_int32), ("tol", C.c_double), ("seed", C.c_uint64),
-                ("cg_max_iters", C.c_int32), ("reserved", C.c_int32), ("cg_tol", C.c_double)]
+                ("cg_max_iters", C.c_int32), ("klda_path", C.c_int32), ("cg_tol", C.c_double)]
 
 
 class Stats(C.Structure):

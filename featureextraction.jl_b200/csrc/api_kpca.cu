@@ -271,9 +271,12 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     if (rows_valid > ld) rows_valid = ld;
     const int64_t d_pad = round_up(d, 16);
     const int kp = (int)round_up(k, 8);
-    const bool dense = (n <= 256) || (k > 64) || (n < 8 * (int64_t)o.block);
-    if (dense && n > 1024) {
-        fx_set_error("kpca_fit: k=%d > 64 components is only supported for n <= 1024 (dense path)", k);
+    // dense Jacobi for tiny problems; k > 64 beyond that: groups of 64 with locking (below)
+    const bool dense = (n <= 256) || (n < 8 * (int64_t)o.block) || (k > 64 && n <= 1024);
+    const bool grouped = !dense && k > 64;
+    if (grouped && k > 1024) {
+        fx_set_error("kpca_fit: k=%d > 1024 components for n > 1024 is not supported (the reference's all-n "
+                     "request, common.jl:164, is served for n <= 1024)", k);
         return -8;
     }
     if (!dense) {
@@ -285,7 +288,7 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     size_t need = fx_gramstage_bytes(ld, n_ld, d_pad, center != 0);
     need += fx_align256((size_t)kp * n_ld * 8) + fx_align256((size_t)(kp + 8) * 8) + 4096;
     if (dense) need += 3 * fx_align256((size_t)n * n * 8) + fx_align256((size_t)n_ld * n_ld * 8) + 8192;
-    else need += fx_eig_workspace_bytes(ctx, ld, n_ld, k, o);
+    else need += fx_eig_workspace_bytes(ctx, ld, n_ld, k, o) + (grouped ? fx_align256((size_t)kp * ld * 8) : 0);
     FX_TRY(fx_arena_reserve(ctx, need));
     fx_arena_reset(ctx);
 
@@ -310,7 +313,46 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     ea.rows_valid = rows_valid; ea.k = k; ea.opts = o; ea.Vout = Vout; ea.theta = theta;
     if (g.defer_center) { ea.center_colmean = g.colmean; ea.center_grand = g.scal; }
     tm.begin(&st->eig_ms);
-    int eig_rc = dense ? fx_eig_dense(ctx, ea, tm, st) : fx_eig_topk(ctx, ea, tm, st);
+    int eig_rc = 0;
+    if (dense) {
+        eig_rc = fx_eig_dense(ctx, ea, tm, st);
+    } else if (!grouped) {
+        eig_rc = fx_eig_topk(ctx, ea, tm, st);
+    } else {
+        // k > 64: the spectrum is taken in groups of 64.  Converged eigenvectors are LOCKED: every later
+        // group iterates in their orthogonal complement, i.e. on the deflated operator, whose leading
+        // pairs are the next ones of K~ (descending order overall, like common.jl:164).
+        double* Lloc = (double*)fx_arena_alloc(ctx, (size_t)kp * ld * 8);
+        if (!Lloc) { fx_set_error("internal: arena too small"); return FX_ERR_OOM; }
+        FX_CUDA(cudaMemsetAsync(Lloc, 0, (size_t)kp * ld * 8, s));
+        const size_t mark = ctx->arena_off;
+        int done = 0, steps = 0, restarts = 0;
+        double scale_ref = 0.0, worst = 0.0;
+        while (done < k && (eig_rc == 0 || eig_rc == FX_ERR_NOT_CONVERGED)) {
+            const int kg = (k - done) < 64 ? (k - done) : 64;
+            EigArgs eg = ea;
+            eg.k = kg; eg.Vout = Vout + (size_t)done * n_ld; eg.theta = theta + done;
+            eg.lock = Lloc; eg.nlock = done; eg.scale_ref = scale_ref;
+            if (done > 0) { eg.center_colmean = nullptr; eg.center_grand = nullptr; }   // K is centred by now
+            ctx->arena_off = mark;                                  // the solver carves its workspace anew
+            const int rc = fx_eig_topk(ctx, eg, tm, st);
+            if (rc != 0 && rc != FX_ERR_NOT_CONVERGED) { eig_rc = rc; break; }
+            if (rc == FX_ERR_NOT_CONVERGED) eig_rc = rc;
+            steps += st->steps; restarts += st->restarts;
+            if (st->max_residual > worst) worst = st->max_residual;
+            const int kgp = (int)round_up(kg, 8);
+            FX_CUDA(cudaMemcpy2DAsync(Lloc + (size_t)done * ld, ld * 8, eg.Vout + row0, n_ld * 8, ld * 8, kgp,
+                                      cudaMemcpyDeviceToDevice, s));
+            if (done == 0) {
+                FX_CUDA(cudaMemcpyAsync(ctx->pinned + 96, theta, sizeof(double), cudaMemcpyDeviceToHost, s));
+                FX_CUDA(cudaStreamSynchronize(s));
+                scale_ref = fabs(ctx->pinned[96]);
+            }
+            done += kg;
+        }
+        st->steps = steps; st->restarts = restarts; st->max_residual = worst;
+        st->converged = (eig_rc == 0) ? 1 : 0;
+    }
     tm.end();
     if (eig_rc != 0 && eig_rc != FX_ERR_NOT_CONVERGED) return eig_rc;
     if (g.defer_center) FX_TRY(fx_gramstage_trace(ctx, g, tm, st));

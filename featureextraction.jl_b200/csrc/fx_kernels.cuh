@@ -148,6 +148,13 @@ struct EigArgs {
     // K*V pass centres it in place (symm.cu CENTER variant); K is centred when the call returns.
     const double* center_colmean = nullptr;
     const double* center_grand = nullptr;
+    // Locking (k > 64): `nlock` converged eigenvectors (local rows, column-major, leading dimension
+    // ld) that the iteration is kept orthogonal to -- the solver then returns the NEXT k pairs of the
+    // spectrum.  scale_ref > 0 replaces |theta_1| of this call as the reference of the relative
+    // residual tolerance (the largest eigenvalue of the whole problem).
+    const double* lock = nullptr;
+    int nlock = 0;
+    double scale_ref = 0.0;
 };
 int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st);
 int fx_eig_dense(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st);
@@ -186,6 +193,8 @@ int fx_launch_indicator(fx_ctx* ctx, const int* ydev, int64_t n, int64_t ldr, in
 
 // ---- linear.cu: device core of lda! (shared with the dense path of fx_klda_fit_f64) ---------------
 size_t fx_lda_core_bytes(fx_ctx* ctx, int64_t n, int64_t p);
+int fx_lda_hw_trace(fx_ctx* ctx, double* Xd, int64_t n, int64_t p, int64_t ld, const int64_t* y, int k,
+                    const double* inv_cnt, double* out);
 int fx_lda_core(fx_ctx* ctx, double* Xd, int64_t n, int64_t p, int64_t ld, const int64_t* y, int k,
                 const double* freq, const double* inv_cnt, double alpha_b, double eps_b, double alpha_w,
                 double eps_w, double** Vd_out, int64_t* ldv_out, double** lam_out, int hinfo[8]);

@@ -155,6 +155,99 @@ int fx_launch_indicator(fx_ctx* ctx, const int* ydev, int64_t n, int64_t ldr, in
     return 0;
 }
 
+constexpr int FX_KLDA_DENSE_MAX_N = 512;
+
+// trace of a p x p device matrix with leading dimension ld (one CTA)
+__global__ void diag_trace_kernel(const double* M, long ld, int p, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < p; i += blockDim.x) s += M[i + (long)i * ld];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) *out = t;
+    }
+}
+
+// Dense KLDA for n <= FX_KLDA_DENSE_MAX_N: K = k(X, X) by the Gram kernel, then lda! on K as the data
+// matrix (fx_lda_core: class means of the rows of K, H_w, H_b, Sigma_b / Sigma_w with shrink and
+// perturb, generalized symmetric eigenproblem).  eps_w < 0 means |eps_w| tr(Sigma_w) / n.
+static int klda_dense(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx, int kernel_id,
+                      const double* kpv, const int64_t* y, int c, const double* freq, const double* inv_cnt,
+                      double alpha_b, double eps_b, double alpha_w, double eps_w, int ncomp, int variant,
+                      double* A, int64_t lda, double* lambda, fx_model** model, fx_stats* st, int64_t launches0) {
+    const int64_t ld = round_up(n, 128), d_pad = round_up(d, 16);
+    const int ncp = (int)round_up(ncomp, 8);
+    size_t need = fx_gramstage_bytes(ld, ld, d_pad, false) + fx_lda_core_bytes(ctx, n, n) +
+                  2 * fx_align256((size_t)ld * ld * 8) + fx_align256((size_t)ncp * ld * 8) + 65536;
+    FX_TRY(fx_arena_reserve(ctx, need));
+    fx_arena_reset(ctx);
+    cudaStream_t s = ctx->stream;
+    cudaEvent_t e0, e1;
+    FX_CUDA(cudaEventCreate(&e0));
+    FX_CUDA(cudaEventCreate(&e1));
+    FX_CUDA(cudaEventRecord(e0, s));
+    FxTimer tm(ctx);
+    GramStage g;
+    g.n = n; g.d = d; g.ld = ld; g.n_ld = ld; g.d_pad = d_pad; g.row0 = 0; g.rows_valid = n;
+    FX_TRY(fx_gramstage_run(ctx, g, X, false, ldx, kernel_id, kpv, false, variant, tm, st));
+    double eps_abs = eps_w;
+    if (eps_w < 0.0) {
+        // relative perturbation: needs tr(Sigma_w) = |H_w|_F^2, from a throw-away copy of K
+        double* Kc = (double*)fx_arena_alloc(ctx, (size_t)ld * ld * 8);
+        double* dtr = (double*)fx_arena_alloc(ctx, 256);
+        if (!Kc || !dtr) { fx_set_error("internal: arena too small for dense KLDA"); return FX_ERR_OOM; }
+        FX_CUDA(cudaMemcpyAsync(Kc, g.K, (size_t)ld * ld * 8, cudaMemcpyDeviceToDevice, s));
+        double* Vt = nullptr; double* lt = nullptr; int64_t ldt = 0; int hi[8];
+        // a cheap way to the trace: run the core with unit regularisation and read tr(H_w'H_w) = sum of squares
+        // of H_w -- instead, compute it directly: H_w = (K - M[y]) / (n - c) is what the core leaves in Kc
+        (void)Vt; (void)lt; (void)ldt; (void)hi;
+        FX_TRY(fx_lda_hw_trace(ctx, Kc, n, n, ld, y, c, inv_cnt, dtr));
+        FX_CUDA(cudaMemcpyAsync(ctx->pinned + 200, dtr, 8, cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaStreamSynchronize(s));
+        st->trace = ctx->pinned[200];
+        eps_abs = -eps_w * ctx->pinned[200] / (double)n;
+    }
+    double* Vd = nullptr; double* lam = nullptr; int64_t ldv = 0;
+    int hinfo[8] = {0};
+    tm.begin(&st->eig_ms);
+    FX_TRY(fx_lda_core(ctx, g.K, n, n, ld, y, c, freq, inv_cnt, alpha_b, eps_b, alpha_w, eps_abs, &Vd, &ldv, &lam, hinfo));
+    tm.end();
+    // components: the leading ncomp generalized eigenvectors, as an [ncp][ld] block for the model
+    double* Aout = (double*)fx_arena_alloc(ctx, (size_t)ncp * ld * 8);
+    if (!Aout) { fx_set_error("internal: arena too small for dense KLDA"); return FX_ERR_OOM; }
+    FX_CUDA(cudaMemsetAsync(Aout, 0, (size_t)ncp * ld * 8, s));
+    FX_CUDA(cudaMemcpy2DAsync(Aout, ld * 8, Vd, ldv * 8, n * 8, ncomp, cudaMemcpyDeviceToDevice, s));
+    tm.begin(&st->d2h_ms);
+    FX_CUDA(cudaMemcpy2DAsync(A, lda * 8, Aout, ld * 8, n * 8, ncomp, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(lambda, lam, ncomp * 8, cudaMemcpyDeviceToHost, s));
+    tm.end();
+    st->d2h_bytes += n * ncomp * 8 + ncomp * 8;
+    if (model && !hinfo[4] && hinfo[1] && hinfo[3])
+        FX_TRY(fx_model_build(ctx, g, kernel_id, kpv, ncomp, Aout, false, true, model));
+    FX_CUDA(cudaEventRecord(e1, s));
+    FX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    st->total_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    tm.resolve();
+    st->dense_path = 1;
+    st->block = 0;
+    st->kernel_launches = ctx->launches - launches0;
+    if (hinfo[4]) {
+        fx_set_error("klda_fit: regularised Sigma_w is not positive definite (the analogue of sygvd info > n)");
+        return FX_ERR_NOT_POSDEF;
+    }
+    if (!hinfo[1] || !hinfo[3]) { fx_set_error("klda_fit: dense Jacobi did not converge"); return FX_ERR_NOT_CONVERGED; }
+    st->converged = 1;
+    return 0;
+}
+
 extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx,
                                int kernel_id, const double* kparams, const int64_t* y, int nclass,
                                const double* freq, double alpha_b, double eps_b, double alpha_w,
@@ -178,9 +271,16 @@ extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t 
     const int c = nclass;
     if (c < 2 || c > 64 || c >= n) { fx_set_error("klda_fit: nclass must lie in 2..64 and be < n"); return -9; }
     if (!freq) { fx_set_error("fx_klda_fit_f64: invalid argument 10 (!freq)"); return -10; }
-    if (alpha_b != 0.0 || eps_b != 0.0) {
-        fx_set_error("klda_fit: alpha_b / eps_b != 0 is not supported (Sigma_b must stay rank <= c for the "
-                     "reduced c x c eigenproblem)");
+    // Small problems take the DENSE path: the reference's LDA pipeline applied literally to the n x n
+    // kernel matrix (Sigma_b, Sigma_w formed, generalized eigenproblem by two device Jacobi solves, the
+    // sygvd recipe of common.jl:168-174).  It answers whatever the conditioning of the pencil and
+    // supports alpha_b, eps_b (klda.jl:36-37); the iterative path below needs Sigma_b of rank <= c.
+    const bool dense = n <= FX_KLDA_DENSE_MAX_N && (ctx->world <= 1) && !(opts && opts->klda_path == 1);
+    if (!(alpha_b >= 0.0 && alpha_b <= 1.0)) { fx_set_error("klda_fit: alpha_b must lie in [0,1]"); return -11; }
+    if (!(eps_b >= 0.0)) { fx_set_error("klda_fit: eps_b must be >= 0"); return -12; }
+    if (!dense && (alpha_b != 0.0 || eps_b != 0.0)) {
+        fx_set_error("klda_fit: alpha_b / eps_b != 0 needs the dense path (n <= %d on one GPU): beyond it Sigma_b "
+                     "must stay of rank <= c for the reduced c x c eigenproblem", FX_KLDA_DENSE_MAX_N);
         return alpha_b != 0.0 ? -11 : -12;
     }
     if (!(alpha_w >= 0.0 && alpha_w < 1.0)) { fx_set_error("klda_fit: alpha_w must lie in [0,1)"); return -13; }
@@ -189,7 +289,7 @@ extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t 
                      "(relative: |eps_w| tr(Sigma_w)/n) or alpha_w > 0");
         return FX_ERR_NOT_POSDEF;
     }
-    if (ncomp < 1 || ncomp > c) { fx_set_error("klda_fit: ncomp must lie in 1..nclass"); return -15; }
+    if (ncomp < 1 || ncomp > (dense ? n : c)) { fx_set_error("klda_fit: ncomp must lie in 1..nclass"); return -15; }
     if (!A) { fx_set_error("fx_klda_fit_f64: invalid argument 17 (!A)"); return -17; }
     if (lda < n) { fx_set_error("klda_fit: lda < n (DimensionMismatch)"); return -18; }
     if (!lambda) { fx_set_error("fx_klda_fit_f64: invalid argument 19 (!lambda)"); return -19; }
@@ -219,6 +319,8 @@ extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t 
     if (rows_valid > ld) rows_valid = ld;
     const int64_t d_pad = round_up(d, 16);
     const int cp = (int)round_up(c, 8), ncp = (int)round_up(ncomp, 8);
+    if (dense) return klda_dense(ctx, X, n, d, ldx, kernel_id, kpv, y, c, hfreq.data(), inv_cnt.data(), alpha_b, eps_b,
+                                 alpha_w, eps_w, ncomp, variant, A, lda, lambda, model, st, launches0);
     const int splits = fx_symm_splits(ctx, ld, n_ld);
     const size_t blk = fx_align256((size_t)cp * ld * 8);
     const size_t tnscr = fx_ts_tn_scratch(ctx, cp, cp, ld);

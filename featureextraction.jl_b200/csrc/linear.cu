@@ -69,6 +69,13 @@ __global__ void lda_tables_kernel(const double* sums, int kp, int k, int p, int 
             Hb[(long)j * ldh + c] = (j < p) ? sqrt(freq[c]) * (means[c + (long)j * kp] - m) : 0.0;
     }
 }
+// sums[c][j] *= inv_cnt[c]  (class sums -> class means, kp x pp column-major)
+__global__ void scale_class_rows_kernel(double* sums, int kp, int k, int pp, const double* inv_cnt) {
+    for (int idx = threadIdx.x; idx < kp * pp; idx += blockDim.x) {
+        const int c = idx % kp;
+        sums[idx] = (c < k) ? sums[idx] * inv_cnt[c] : 0.0;
+    }
+}
 // Y[:, j] = U[:, j] / sqrt(d_j); flags non-positive d (B not positive definite)
 __global__ void scale_cols_kernel(const double* U, int ldu, const double* d, int p, double* Y, long ldy, int* bad) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *bad = 0;
@@ -230,6 +237,52 @@ size_t fx_lda_core_bytes(fx_ctx* ctx, int64_t n, int64_t p) {
     if (s3 > s) s = s3;
     return fx_align256(s * 8) + fx_align256((size_t)64 * ld * 8) + 10 * fx_align256((size_t)pp * ldy * 8) +
            fx_align256((size_t)ld * 4) + 65536;
+}
+
+// *out (device) = tr(H_w'H_w) with H_w = (X - M[y]) / (n - k) (klda.jl:49-50); Xd (ld x pp) is destroyed.
+__global__ void sumsq_kernel(const double* __restrict__ X, long total, double scale, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (long i = threadIdx.x; i < total; i += blockDim.x) s = fma(X[i], X[i], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) *out = t * scale;
+    }
+}
+int fx_lda_hw_trace(fx_ctx* ctx, double* Xd, int64_t n, int64_t p, int64_t ld, const int64_t* y, int k,
+                    const double* inv_cnt, double* out) {
+    cudaStream_t s = ctx->stream;
+    const int pp = (int)round_up(p, 8), kp = (int)round_up(k, 8);
+    auto dalloc = [&](size_t d) { return (double*)fx_arena_alloc(ctx, d * 8); };
+    const size_t scr_doubles = fx_ts_tn_scratch(ctx, 64, pp, ld);
+    double* scr = dalloc(scr_doubles);
+    double* E = dalloc((size_t)kp * ld);
+    double* sums = dalloc((size_t)kp * pp);
+    double* dinv = dalloc(64);
+    int* ydev = (int*)fx_arena_alloc(ctx, (size_t)ld * 4);
+    if (!scr || !E || !sums || !dinv || !ydev) { fx_set_error("internal: arena too small for tr(Sigma_w)"); return FX_ERR_OOM; }
+    {
+        std::vector<int> y32(ld, 0);
+        for (int64_t i = 0; i < n; ++i) y32[i] = (int)y[i];
+        FX_CUDA(cudaMemcpyAsync(ydev, y32.data(), (size_t)ld * 4, cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaMemcpyAsync(dinv, inv_cnt, k * 8, cudaMemcpyHostToDevice, s));
+        FX_CUDA(cudaStreamSynchronize(s));
+    }
+    FX_TRY(fx_launch_indicator(ctx, ydev, n, ld, kp, E));
+    FX_TRY(fx_launch_ts_tn(ctx, E, kp, Xd, pp, ld, ld, sums, kp, scr, scr_doubles, 0));
+    scale_class_rows_kernel<<<1, 256, 0, s>>>(sums, kp, k, pp, dinv);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    FX_TRY(fx_launch_ts_nn(ctx, E, kp, sums, kp, pp, -1.0, 1.0, Xd, ld, ld, 0));          // X -= E * means
+    const double sc = 1.0 / ((double)(n - k) * (double)(n - k));
+    sumsq_kernel<<<1, 1024, 0, s>>>(Xd, (long)pp * ld, sc, out);
+    ctx->launches++;
+    FX_LAUNCH_CHECK();
+    return 0;
 }
 
 int fx_lda_core(fx_ctx* ctx, double* Xd, int64_t n, int64_t p, int64_t ld, const int64_t* y, int k,

@@ -33,10 +33,12 @@ void fx_resolve_opts(const fx_solver_opts* in, int k, fx_solver_opts* out) {
     *out = o;
 }
 
+constexpr int FX_MAX_LOCK = 1024;                   // locked vectors a call can be deflated against
+
 namespace {
 struct Work {
     int b, mcap, mt;
-    double *Q, *Wa, *Wb, *Vg, *Ypart, *T, *Tw, *S, *Jw, *theta, *H, *H2, *G, *Gs, *U, *Uw, *lamb,
+    double *Q, *Wa, *Wb, *Vg, *Ypart, *T, *Tw, *S, *Jw, *theta, *H, *H2, *HL, *G, *Gs, *U, *Uw, *lamb,
         *dscale, *M1, *C1, *M2, *C2, *C, *res, *tnscr;
     int* info;
     size_t tnscr_doubles;
@@ -53,7 +55,7 @@ size_t carve(fx_ctx* ctx, int64_t ld, int64_t n_ld, int k, const fx_solver_opts&
     };
     const int splits = fx_symm_splits(ctx, ld, n_ld);
     size_t tn = 0;
-    for (int ma = 8; ma <= mt; ma += 8) {           // chunk count depends on ma: take the max
+    for (int ma = 8; ma <= (mt > FX_MAX_LOCK ? mt : FX_MAX_LOCK); ma += 8) {   // chunk count depends on ma: take the max
         const size_t t1 = fx_ts_tn_scratch(ctx, ma, b, ld);
         if (t1 > tn) tn = t1;
     }
@@ -69,6 +71,7 @@ size_t carve(fx_ctx* ctx, int64_t ld, int64_t n_ld, int k, const fx_solver_opts&
     double* theta = take(mt);
     double* H = take((size_t)mt * b);
     double* H2 = take((size_t)(mt + b) * b);        // stacked [Q W]'W: mq coefficient rows + the b x b Gram
+    double* HL = take((size_t)FX_MAX_LOCK * b);     // coefficients against the locked vectors
     double* G = take(64 * 64); double* Gs = take(64 * 64); double* U = take(64 * 64);
     double* Uw = take(64 * 64); double* lamb = take(64); double* dscale = take(64);
     double* M1 = take(64 * 64); double* C1 = take(64 * 64); double* M2 = take(64 * 64);
@@ -79,7 +82,7 @@ size_t carve(fx_ctx* ctx, int64_t ld, int64_t n_ld, int k, const fx_solver_opts&
     if (w) {
         w->b = b; w->mcap = mcap; w->mt = mt; w->Q = Q; w->Wa = Wa; w->Wb = Wb; w->Vg = Vg;
         w->Ypart = Yp; w->T = T; w->Tw = Tw; w->S = S; w->Jw = Jw; w->theta = theta; w->H = H;
-        w->H2 = H2; w->G = G; w->Gs = Gs; w->U = U; w->Uw = Uw; w->lamb = lamb; w->dscale = dscale;
+        w->H2 = H2; w->HL = HL; w->G = G; w->Gs = Gs; w->U = U; w->Uw = Uw; w->lamb = lamb; w->dscale = dscale;
         w->M1 = M1; w->C1 = C1; w->M2 = M2; w->C2 = C2; w->C = C; w->res = res; w->tnscr = tnscr;
         w->tnscr_doubles = tn; w->info = info; w->splits = splits;
     }
@@ -138,6 +141,25 @@ int project_out(fx_ctx* ctx, const Work& w, int mq, double* W, int64_t ld, doubl
     return 0;
 }
 
+// W -= L (L'W) for the locked eigenvectors (deflation); one CGS pass
+int project_lock(fx_ctx* ctx, const Work& w, const double* L, int nlock, double* W, int64_t ld, int variant,
+                 FxTimer& tm, fx_stats* st) {
+    if (nlock <= 0) return 0;
+    const int b = w.b;
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_tn(ctx, L, nlock, W, b, ld, ld, w.HL, nlock, w.tnscr, w.tnscr_doubles, variant));
+    tm.end();
+    if (ctx->world > 1) {
+        tm.begin(&st->comm_ms);
+        FX_TRY(fxcomm_allreduce_sum(ctx->comm, w.HL, (size_t)nlock * b, ctx->stream));
+        tm.end();
+    }
+    tm.begin(&st->ortho_ms);
+    FX_TRY(fx_launch_ts_nn(ctx, L, nlock, w.HL, nlock, b, -1.0, 1.0, W, ld, ld, variant));
+    tm.end();
+    return 0;
+}
+
 // One reduction for a re-projection and the block Gram matrix that follows it:
 //   Hs = [Q(:, :mq) W]' W  ((mq + b) x b, one all-reduce), then  G = W'W - H2'H2  is the Gram matrix
 // of W - Q H2 (Q orthonormal; H2 is a SECOND-pass coefficient block, tiny, so the subtraction does
@@ -186,8 +208,13 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
     FX_CUDA(cudaMemsetAsync(w.T, 0, (size_t)mt * mt * 8, s));
 
     // start block: deterministic hash noise (independent of the number of ranks), SVQB twice
-    FX_TRY(fx_launch_hash_fill(ctx, w.Wa, ld, a.rows_valid, a.row0, b, o.seed));
+    const int nlock = (int)round_up(a.nlock, 8);       // the caller pads the locked block with zero columns
+    if (nlock > FX_MAX_LOCK) { fx_set_error("eigensolver: more than %d locked vectors", FX_MAX_LOCK); return -1; }
+    FX_TRY(fx_launch_hash_fill(ctx, w.Wa, ld, a.rows_valid, a.row0, b, o.seed + (uint64_t)a.nlock));
+    FX_TRY(project_lock(ctx, w, a.lock, nlock, w.Wa, ld, variant, tm, st));
+    FX_TRY(project_lock(ctx, w, a.lock, nlock, w.Wa, ld, variant, tm, st));
     FX_TRY(svqb_pass(ctx, w, w.Wa, w.Wb, ld, w.M1, w.C1, variant, tm, st));
+    FX_TRY(project_lock(ctx, w, a.lock, nlock, w.Wb, ld, variant, tm, st));
     FX_TRY(svqb_pass(ctx, w, w.Wb, w.Q, ld, w.M2, w.C2, variant, tm, st));
 
     int m = 0, steps = 0, restarts = 0;
@@ -240,7 +267,9 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
         steps++;
         // 3-5. CGS2 against [Q Qn]; H accumulates both passes.  The second pass shares its reduction
         // with the Gram matrix of the block orthonormalisation (3 collectives per step, not 5).
+        FX_TRY(project_lock(ctx, w, a.lock, nlock, w.Wa, ld, variant, tm, st));
         FX_TRY(project_out(ctx, w, mq, w.Wa, ld, w.H, variant, tm, st));
+        FX_TRY(project_lock(ctx, w, a.lock, nlock, w.Wa, ld, variant, tm, st));
         FX_TRY(reproject_and_orthonormalise(ctx, w, mq, w.Wa, w.Wb, ld, w.H2, w.M1, w.C1, variant, tm, st));
         FX_TRY(fx_launch_copy2d_add(ctx, w.H2, mq + b, w.H, mq, mq, b));          // H += H2 (leading mq rows)
         // 6. projected matrix
@@ -281,7 +310,7 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
         }
         FX_CUDA(cudaEventSynchronize(ctx->ev_join));
         FX_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));      // T, S, theta are free for the main stream again
-        const double scale = fabs(pinned[64]) > 1e-300 ? fabs(pinned[64]) : 1e-300;
+        const double scale = a.scale_ref > 0.0 ? a.scale_ref : (fabs(pinned[64]) > 1e-300 ? fabs(pinned[64]) : 1e-300);
         maxres = 0.0;
         bool finite = true;
         for (int i = 0; i < k; ++i) {

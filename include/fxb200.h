@@ -63,7 +63,7 @@ typedef struct fx_solver_opts {
     double  tol;          /* Ritz residual tolerance relative to |theta_1| (default 1e-12)   */
     uint64_t seed;        /* start-block seed (default 0x5eed)                               */
     int32_t cg_max_iters; /* KLDA: CG iterations allowed (default 4000)                      */
-    int32_t reserved;
+    int32_t klda_path;    /* KLDA: 0 = automatic (dense pipeline for n <= 512 on one GPU), 1 = force the iterative path */
     double  cg_tol;       /* KLDA: CG relative residual (default 1e-10)                      */
 } fx_solver_opts;
 

@@ -284,7 +284,7 @@ def test_klda_matches_oracle(gpu_ctx, n, d, c, rel):
     eps_w = rel * np.trace(Sw) / n
     Ao, Lo = O.klda(X, okern, y, c, freq, eps_w=eps_w)
     A, L, model, st = fxb200.klda(X, kern, y, c, freq, eps_w=eps_w, ctx=gpu_ctx, return_model=True,
-                                  return_stats=True)
+                                  return_stats=True, opts=fxb200.make_opts(klda_path=1))   # iterative path
     assert st["converged"] == 1 and st["cg_iters"] > 0
     np.testing.assert_allclose(L, Lo, rtol=1e-7)
     # vectors: compare the spanned subspace (clustered eigenvalues) and the B-normalisation
@@ -292,7 +292,7 @@ def test_klda_matches_oracle(gpu_ctx, n, d, c, rel):
     Swr = Sw + eps_w * np.eye(n)
     np.testing.assert_allclose(np.diag(A.T @ Swr @ A), 1.0, rtol=1e-6)
     # relative eps_w (negative) resolves to the same problem
-    A2, L2 = fxb200.klda(X, kern, y, c, freq, eps_w=-rel, ctx=gpu_ctx)
+    A2, L2 = fxb200.klda(X, kern, y, c, freq, eps_w=-rel, ctx=gpu_ctx, opts=fxb200.make_opts(klda_path=1))
     np.testing.assert_allclose(L2, Lo, rtol=1e-6)
     # transform_klda = k(Z,X) A, no centring (klda.jl:71)
     Z, _ = mix(77, d, c, 2.0, 72)
@@ -308,7 +308,7 @@ def test_klda_alpha_w_and_errors(gpu_ctx):
     X, y, freq = _klda_case(n, d, c, 2.0, 73, 1.0 / d)
     kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
     Ao, Lo = O.klda(X, okern, y, c, freq, alpha_w=0.05)
-    A, L = fxb200.klda(X, kern, y, c, freq, alpha_w=0.05, ctx=gpu_ctx)
+    A, L = fxb200.klda(X, kern, y, c, freq, alpha_w=0.05, ctx=gpu_ctx, opts=fxb200.make_opts(klda_path=1))
     np.testing.assert_allclose(L, Lo, rtol=1e-7)
     ybad = y.copy(); ybad[3] = c + 1
     with pytest.raises(ValueError):                     # klda.jl:8 "Index out of range"
@@ -320,8 +320,15 @@ def test_klda_alpha_w_and_errors(gpu_ctx):
     # an ill-conditioned pencil that CG cannot finish in the allowed iterations reports
     # "not converged" (the analogue of LAPACKException, common.jl:90-92) instead of a wrong answer
     with pytest.raises(fxb200.FxError) as ei:
-        fxb200.klda(X, kern, y, c, freq, eps_w=-1e-9, ctx=gpu_ctx, opts=fxb200.make_opts(cg_max_iters=20))
+        fxb200.klda(X, kern, y, c, freq, eps_w=-1e-9, ctx=gpu_ctx, opts=fxb200.make_opts(cg_max_iters=20, klda_path=1))
     assert ei.value.code == 4
+    # ... while the dense path (the default at this size) answers the same ill-conditioned pencil like sygvd
+    H_b, H_w, _ = O.lda_matrices(O.kernelmatrix(okern, X), y, c, freq)
+    tr_w = np.trace(O.scatter_matrices(H_b, 0, 0, H_w, 0, 0)[1])
+    Ao, Lo = O.klda(X, okern, y, c, freq, eps_w=1e-9 * tr_w / n)
+    A, L, st = fxb200.klda(X, kern, y, c, freq, eps_w=-1e-9, ctx=gpu_ctx, return_stats=True)
+    assert st["dense_path"] == 1
+    np.testing.assert_allclose(L, Lo, rtol=1e-4)
 
 
 # ------------------------------------------------------------------ edge cases
@@ -340,6 +347,28 @@ def test_kpca_shapes(gpu_ctx, n, d, k):
     kk = min(k, 3)                      # leading, well separated part
     assert sin_angle(V[:, :kk], Vo[:, :kk]) < 1e-7
     assert st["dense_path"] == (1 if (n <= 256 or k > 64) else 0)
+
+
+@pytest.mark.parametrize("n,d,k", [(4096, 64, 256), (2048, 16, 200), (1500, 8, 70)])
+def test_kpca_more_than_64_components(gpu_ctx, n, d, k):
+    """k > 64 beyond the dense-Jacobi sizes: groups of 64 with locked (deflated) eigenvectors.  All k
+    eigenvalues against dsyevd (the reference returns every pair, common.jl:164), orthonormality, the
+    eigen-residual of every returned pair, and the subspace of the well separated leading part."""
+    X, _ = mix(n, d, 9, 3.0, 92)
+    kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+    V, L, model, st = fxb200.kpca(X, kern, k=k, ctx=gpu_ctx, return_model=True, return_stats=True)
+    Vo, Lo = O.kpca(X, okern)
+    assert st["converged"] == 1 and st["dense_path"] == 0
+    assert np.abs(L - Lo[:k]).max() <= 1e-10 * Lo[0]
+    assert np.all(np.diff(L) <= 1e-12 * Lo[0])
+    assert np.abs(V.T @ V - np.eye(k)).max() < 1e-10
+    Kc, _, _ = O.centerkernelmatrix(O.kernelmatrix(okern, X))
+    R = Kc @ V - V * (L * (n - 1))[None, :]
+    assert np.abs(R).max() <= 1e-9 * Lo[0] * (n - 1)
+    assert sin_angle(V[:, :8], Vo[:, :8]) < 1e-8
+    Z, _ = mix(50, d, 9, 3.0, 93)
+    relclose(model.transform(Z), O.transform_kpca(X, okern, V, Z), 1e-9)        # k > 64 through the model
+    model.free()
 
 
 def test_kpca_degenerate_inputs(gpu_ctx):
@@ -459,6 +488,35 @@ def test_kpca_tiny(gpu_ctx, n, d):
         assert V.shape == (n, n)
         assert np.abs(L - Lo).max() <= 1e-12 * max(np.abs(Lo).max(), 1e-300)
         assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,d,c", [(300, 6, 3), (500, 12, 5), (512, 20, 10)])
+def test_klda_dense_path_matches_sygvd(gpu_ctx, n, d, c):
+    """n <= 512: the reference's LDA pipeline applied literally to K (klda.jl:34-61 with the intended
+    pencil), including the between-class regularisation alpha_b, eps_b (klda.jl:36-37) that the
+    reduced iterative path cannot take -- against the oracle's dsygvd, all n components."""
+    X, y, freq = _klda_case(n, d, c, 2.0, 74, 1.0 / d)
+    kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+    K = O.kernelmatrix(okern, X)
+    H_b, H_w, _ = O.lda_matrices(K, y, c, freq)
+    for (ab, eb, aw, ew_rel) in [(0.0, 0.0, 0.0, 1e-4), (0.2, 0.01, 0.1, 1e-3), (0.0, 1e-3, 0.0, 1e-2)]:
+        _Sb0, Sw0 = O.scatter_matrices(H_b, 0, 0, H_w, 0, 0)
+        ew = ew_rel * np.trace(Sw0) / n
+        Ao, Lo = O.klda(X, okern, y, c, freq, ab, eb, aw, ew, ncomp=n)
+        ncomp = n if (ab or eb) else c - 1
+        A, L, model, st = fxb200.klda(X, kern, y, c, freq, ab, eb, aw, ew, ncomp=ncomp, ctx=gpu_ctx,
+                                      return_model=True, return_stats=True)
+        assert st["dense_path"] == 1 and st["converged"] == 1
+        scale = np.abs(Lo).max()
+        assert np.abs(L - Lo[:ncomp]).max() <= 1e-8 * scale
+        Sb, Sw = O.scatter_matrices(H_b, ab, eb, H_w, aw, ew)
+        kk = min(ncomp, c - 1)
+        R = Sb @ A[:, :kk] - (Sw @ A[:, :kk]) * L[None, :kk]
+        assert (np.linalg.norm(R, axis=0) / np.linalg.norm(Sb @ A[:, :kk], axis=0)).max() < 1e-7
+        np.testing.assert_allclose(A[:, :kk].T @ Sw @ A[:, :kk], np.eye(kk), atol=1e-7)
+        Z, _ = mix(33, d, c, 2.0, 75)
+        relclose(model.transform(Z), O.transform_klda(X, okern, A, Z), 1e-10)
+        model.free()
 
 
 def test_klda_orphan_test_sizes(gpu_ctx):
