@@ -78,6 +78,34 @@ __device__ __forceinline__ void gram_epilogue_plain(const GramParams& p, double 
                                                     const double (&ni)[8], const double (&nbv)[4][2], long i0,
                                                     long j0, int wm, int wn, int g, int t, double* rsb) {
     const long jb = j0 + wn * 32 + 2 * t;
+    if (KID == 0 && !EDGE) {
+        // interior Gaussian tiles: the 8 elements of a fragment row go through the staged exp together
+        // (8 interleaved dependency chains per warp instead of one after the other)
+        const double two_gamma = 2.0 * p.km.p0;
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+            double* krow = p.K + (i0 + wm * 64 + mt * 8 + g) * p.ldk + jb;
+            double x[8];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                x[2 * nt] = fma(two_gamma, acc[mt][nt][0], ni[mt] + nbv[nt][0]);
+                x[2 * nt + 1] = fma(two_gamma, acc[mt][nt][1], ni[mt] + nbv[nt][1]);
+            }
+            fx_exp_nonpos_vec<8>(x);
+            double sacc = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                *reinterpret_cast<double2*>(krow + nt * 8) = make_double2(x[2 * nt], x[2 * nt + 1]);
+                sacc += x[2 * nt] + x[2 * nt + 1];
+            }
+            if (p.rowpart) {
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                if (t == 0) rsb[wn * BM + wm * 64 + mt * 8 + g] = sacc;
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) {
         const long i = i0 + wm * 64 + mt * 8 + g;
@@ -140,6 +168,33 @@ __device__ __forceinline__ void gram_epilogue_mirror(const GramParams& p, double
             if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncwarp();
         }
+        if (KID == 0 && !EDGE) {
+            // interior Gaussian tiles: 2 x 8 elements through the staged exp (interleaved chains)
+            const double two_gamma = 2.0 * p.km.p0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                double x[8];
+#pragma unroll
+                for (int m4 = 0; m4 < 4; ++m4) {
+                    const int mt = half * 4 + m4;
+                    x[2 * m4] = fma(two_gamma, acc[mt][nt][0], ni[mt] + nb0);
+                    x[2 * m4 + 1] = fma(two_gamma, acc[mt][nt][1], ni[mt] + nb1);
+                }
+                fx_exp_nonpos_vec<8>(x);
+#pragma unroll
+                for (int m4 = 0; m4 < 4; ++m4) {
+                    const int mt = half * 4 + m4;
+                    const long i = i0 + wm * 64 + mt * 8 + g;
+                    const double v0 = x[2 * m4], v1 = x[2 * m4 + 1];
+                    *reinterpret_cast<double2*>(p.K + i * p.ldk + jb + nt * 8) = make_double2(v0, v1);
+                    tb[(2 * t) * TS + mt * 8 + g] = v0;              // transposed: row = column of the tile
+                    tb[(2 * t + 1) * TS + mt * 8 + g] = v1;
+                    cs0 += v0;
+                    cs1 += v1;
+                    sacc[mt] += v0 + v1;
+                }
+            }
+        } else {
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt) {
             const long i = i0 + wm * 64 + mt * 8 + g;
@@ -162,6 +217,7 @@ __device__ __forceinline__ void gram_epilogue_mirror(const GramParams& p, double
             cs0 += v0;
             cs1 += v1;
             sacc[mt] += v0 + v1;
+        }
         }
         {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -51,25 +51,44 @@ __device__ __forceinline__ void transform_map(const KernelMap& km, double (&acc1
                                               const double* __restrict__ nxt, long j0, long n_valid, int t,
                                               bool want_rz, double (&rz)[2]) {
     const double two_g = 2.0 * km.p0, neg_g = -km.p0;
+    if (KID == 0) {
+        // Gaussian: 8 elements (two column blocks) at a time through the staged exp, so that the
+        // dependency chains of the exp are interleaved (fx_exp_nonpos_vec)
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2 += 2) {
+            double x[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double2 v = *reinterpret_cast<const double2*>(nxt + (n2 + h) * 8 + 2 * t);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    x[h * 4 + mt * 2] = fma(two_g, acc1[mt][n2 + h][0], fma(neg_g, v.x, nzs[mt]));
+                    x[h * 4 + mt * 2 + 1] = fma(two_g, acc1[mt][n2 + h][1], fma(neg_g, v.y, nzs[mt]));
+                }
+            }
+            fx_exp_nonpos_vec<8>(x);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        double v = x[h * 4 + mt * 2 + q];
+                        if (EDGE) v = (j0 + (n2 + h) * 8 + 2 * t + q < n_valid) ? v : 0.0;
+                        acc1[mt][n2 + h][q] = v;
+                        if (want_rz) rz[mt] += v;
+                    }
+        }
+        return;
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-        double nx[2] = {0.0, 0.0};
-        if (KID == 0) {
-            const double2 v = *reinterpret_cast<const double2*>(nxt + nt * 8 + 2 * t);
-            nx[0] = v.x; nx[1] = v.y;
-        }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const long j = j0 + nt * 8 + 2 * t + q;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                double v;
-                if (KID == 0) {
-                    // exp(-gamma (|z|^2 + |x|^2 - 2 z'x)), norms folded in with two FMAs
-                    v = fx_exp_nonpos(fma(two_g, acc1[mt][nt][q], fma(neg_g, nx[q], nzs[mt])));
-                } else {
-                    v = kernel_map_t<KID>(km, acc1[mt][nt][q], 0.0, 0.0, false);
-                }
+                double v = kernel_map_t<KID>(km, acc1[mt][nt][q], 0.0, 0.0, false);
                 if (EDGE) v = (j < n_valid) ? v : 0.0;
                 acc1[mt][nt][q] = v;
                 if (want_rz) rz[mt] += v;
@@ -77,7 +96,6 @@ __device__ __forceinline__ void transform_map(const KernelMap& km, double (&acc1
         }
     }
 }
-
 
 template <int NBK, int KID>
 __global__ void __launch_bounds__(288, 1) transform_kernel(const TrParams p) {
