@@ -43,6 +43,7 @@ PROTOTYPES = {
     "fx_init": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "fx_comm_unique_id": (C.c_int, [_P]),
     "fx_init_distributed": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "fx_init_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     "fx_set_stream": (C.c_int, [_P, _P]),
     "fx_ctx_info": (C.c_int, [_P] + [C.POINTER(C.c_int)] * 4),
     "fx_ctx_peer_access": (C.c_int, [_P]),

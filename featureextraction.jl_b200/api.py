@@ -37,6 +37,16 @@ class Context:
               "fx_init_distributed")
         return cls(_handle=h)
 
+    @classmethod
+    def multi(cls, devices):
+        """One process, several GPUs (fx_init_multi): K row-sharded over ``devices`` by the library
+        itself, one host thread per device, NCCL and peer access set up internally."""
+        lib = _lib.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(lib.fx_init_multi(devs, len(devices), C.byref(h)), "fx_init_multi")
+        return cls(_handle=h)
+
     @staticmethod
     def unique_id():
         lib = _lib.load()

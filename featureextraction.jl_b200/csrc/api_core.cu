@@ -1,6 +1,7 @@
 // api_core.cu -- contexts, error text, device arena, event timers.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <thread>
 #include "fx_kernels.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -54,7 +55,45 @@ void fx_peer_close_all(fx_ctx* ctx) {
     ctx->peer_valid = false;
 }
 
+// In-process variant (fx_init_multi): the rank threads meet on a host barrier and hand each other
+// plain device pointers (unified addressing + cudaDeviceEnablePeerAccess, no IPC handles).
+static int fx_peer_exchange_inproc(fx_ctx* ctx, size_t off0, size_t off1) {
+    ctx->peer_valid = false;
+    const int G = ctx->world, r = ctx->rank;
+    FxMultiShared* ms = ctx->parent->ms;
+    static const bool disabled = []() { const char* e = getenv("FXB200_NO_PEER"); return e && e[0] == '1'; }();
+    int ok = (!disabled && G <= fx_ctx::MAX_PEERS && ctx->arena) ? 1 : 0;
+    for (int c = 0; c < G && ok; ++c) {
+        if (c == r) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctx->device, ctx->parent->sub[c]->device) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ctx->parent->sub[c]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+        cudaGetLastError();
+    }
+    ms->arena[r] = ctx->arena; ms->off[r][0] = off0; ms->off[r][1] = off1; ms->ok[r] = ok;
+    ms->barrier();
+    bool all_ok = true;
+    for (int c = 0; c < G; ++c) all_ok = all_ok && ms->ok[c];
+    if (all_ok)
+        for (int c = 0; c < G; ++c) {
+            ctx->peer_arena[c] = (c == r) ? nullptr : ms->arena[c];
+            ctx->peer_off[c][0] = ms->off[c][0];
+            ctx->peer_off[c][1] = ms->off[c][1];
+        }
+    ms->barrier();                                         // everybody has read the table
+    if (!all_ok) return 0;
+    // stream-ordered barrier across the ranks: no rank writes into a peer before that peer is done
+    // with its previous use of the buffers
+    if (!ctx->peer_stage) FX_CUDA(cudaMalloc((void**)&ctx->peer_stage, 256));
+    FX_CUDA(cudaMemsetAsync(ctx->peer_stage, 0, 8, ctx->stream));
+    FX_TRY(fxcomm_allreduce_sum(ctx->comm, ctx->peer_stage, 1, ctx->stream));
+    ctx->peer_valid = true;
+    return 0;
+}
+
 int fx_peer_exchange(fx_ctx* ctx, size_t off0, size_t off1) {
+    if (ctx->parent) return fx_peer_exchange_inproc(ctx, off0, off1);
     ctx->peer_valid = false;
     const int G = ctx->world;
     if (G <= 1 || G > fx_ctx::MAX_PEERS || !ctx->comm || ctx->peer_failed) return 0;
@@ -212,6 +251,60 @@ static int ctx_common_init(int device, fx_ctx** out) {
 
 extern "C" int fx_init(int device, fx_ctx** out) { return ctx_common_init(device, out); }
 
+// Single process, several GPUs: one sub-context and one host thread per device,
+// NCCL communicators created in-process, peer access enabled directly.  A Julia caller makes ONE
+// ccall per fit and never sees NCCL or ranks.
+extern "C" int fx_init_multi(const int* devices, int ndev, fx_ctx** out) {
+    if (!out) { fx_set_error("fx_init_multi: out is NULL"); return -3; }
+    *out = nullptr;
+    if (!devices) { fx_set_error("fx_init_multi: devices is NULL"); return -1; }
+    if (ndev < 1 || ndev > fx_ctx::MAX_PEERS) { fx_set_error("fx_init_multi: ndev must lie in 1..%d", fx_ctx::MAX_PEERS); return -2; }
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) { fx_set_error("fx_init_multi: device %d listed twice", devices[i]); return -1; }
+    fx_ctx* parent = new fx_ctx();
+    parent->world = ndev;
+    parent->ms = new FxMultiShared();
+    parent->ms->n = ndev;
+    int rc = 0;
+    for (int i = 0; i < ndev && !rc; ++i) {
+        fx_ctx* c = nullptr;
+        rc = ctx_common_init(devices[i], &c);
+        if (rc) break;
+        c->rank = i; c->world = ndev; c->parent = parent;
+        parent->sub.push_back(c);
+    }
+    if (!rc && ndev > 1) {
+        FxComm* comms[fx_ctx::MAX_PEERS] = {};
+        rc = fxcomm_create_all(devices, ndev, comms);
+        if (!rc) for (int i = 0; i < ndev; ++i) parent->sub[i]->comm = comms[i];
+    }
+    if (rc) { fx_shutdown(parent); return rc; }
+    parent->device = devices[0];
+    parent->sm_count = parent->sub[0]->sm_count;
+    *out = parent;
+    return 0;
+}
+
+// Runs fn(sub-context, rank) on one host thread per device and joins; the first failure's code and
+// message become the caller's.
+int fx_multi_run(fx_ctx* parent, const std::function<int(fx_ctx*, int)>& fn) {
+    const int G = (int)parent->sub.size();
+    std::vector<int> rc(G, 0);
+    std::vector<std::string> msg(G);
+    std::vector<std::thread> th;
+    for (int i = 0; i < G; ++i)
+        th.emplace_back([&, i]() {
+            cudaSetDevice(parent->sub[i]->device);
+            rc[i] = fn(parent->sub[i], i);
+            if (rc[i]) msg[i] = fx_last_error();
+        });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < G; ++i)
+        if (rc[i]) { fx_set_error("%s", msg[i].c_str()); return rc[i]; }
+    return 0;
+}
+
 extern "C" int fx_comm_unique_id(void* id128) {
     if (!id128) { fx_set_error("fx_comm_unique_id: invalid argument 1 (!id128)"); return -1; }
     return fxcomm_unique_id(id128);
@@ -233,6 +326,7 @@ extern "C" int fx_init_distributed(int device, int rank, int world, const void* 
 
 extern "C" int fx_set_stream(fx_ctx* ctx, void* cuda_stream) {
     if (!ctx) { fx_set_error("fx_set_stream: ctx is NULL"); return -1; }
+    if (!ctx->sub.empty()) { fx_set_error("fx_set_stream: a multi-GPU context owns one stream per device"); return -1; }
     cudaSetDevice(ctx->device);
     if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (cuda_stream) {
@@ -254,10 +348,23 @@ extern "C" int fx_ctx_info(const fx_ctx* ctx, int* device, int* rank, int* world
     return 0;
 }
 
-extern "C" int fx_ctx_peer_access(const fx_ctx* ctx) { return (ctx && ctx->peer_valid) ? 1 : 0; }
+extern "C" int fx_ctx_peer_access(const fx_ctx* ctx) {
+    if (ctx && !ctx->sub.empty()) return ctx->sub[0]->peer_valid ? 1 : 0;
+    return (ctx && ctx->peer_valid) ? 1 : 0;
+}
 
 extern "C" void fx_shutdown(fx_ctx* ctx) {
     if (!ctx) return;
+    if (!ctx->sub.empty() || ctx->ms) {
+        for (fx_ctx* c : ctx->sub) {
+            for (int k = 0; k < fx_ctx::MAX_PEERS; ++k) c->peer_arena[k] = nullptr;   // plain pointers, not IPC mappings
+            c->parent = nullptr;
+            fx_shutdown(c);
+        }
+        delete ctx->ms;
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     fx_peer_close_all(ctx);
@@ -276,6 +383,11 @@ extern "C" void fx_shutdown(fx_ctx* ctx) {
 
 extern "C" void fx_model_free(fx_model* m) {
     if (!m) return;
+    if (!m->sub.empty()) {
+        for (fx_model* r : m->sub) fx_model_free(r);
+        delete m;
+        return;
+    }
     cudaSetDevice(m->device);
     cudaFree(m->Xp);
     cudaFree(m->norms);
@@ -288,6 +400,7 @@ extern "C" void fx_model_free(fx_model* m) {
 
 extern "C" int fx_model_info(const fx_model* m, int64_t* n, int64_t* d, int* k, int* kernel_id) {
     if (!m) { fx_set_error("fx_model_info: model is NULL"); return -1; }
+    if (!m->sub.empty()) m = m->sub[0];
     if (n) *n = m->n;
     if (d) *d = m->d;
     if (k) *k = m->k;

@@ -242,9 +242,10 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     if (k < 1 || k > n) { fx_set_error("kpca_fit: k=%d outside 1..n", k); return -8; }
     if (!(alpha >= 0.0 && alpha <= 1.0)) { fx_set_error("kpca_fit: alpha must lie in [0,1]"); return -10; }
     if (!(eps >= 0.0)) { fx_set_error("kpca_fit: eps must be >= 0"); return -11; }
-    if (!V) { fx_set_error("kpca_fit: V is NULL"); return -13; }
+    const bool mute = ctx->parent && ctx->rank != 0;       // in-process rank other than the leader: no host output
+    if (!V && !mute) { fx_set_error("kpca_fit: V is NULL"); return -13; }
     if (ldv < n) { fx_set_error("kpca_fit: ldv < n (DimensionMismatch)"); return -14; }
-    if (!lambda) { fx_set_error("kpca_fit: lambda is NULL"); return -15; }
+    if (!lambda && !mute) { fx_set_error("kpca_fit: lambda is NULL"); return -15; }
 
     FX_CUDA(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
@@ -378,7 +379,9 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     for (int i = 0; i < k; ++i)
         lam[i] = ((1.0 - alpha) * hp[i] + alpha * trace / (double)n + eps * (double)(n - 1)) / (double)(n - 1);
     tm.begin(&st->d2h_ms);
-    if (on_dev) {
+    if (mute) {
+        // results leave through the leader rank
+    } else if (on_dev) {
         for (int i = 0; i < k; ++i) hp[i] = lam[i];
         FX_CUDA(cudaMemcpyAsync(lambda, hp, k * sizeof(double), cudaMemcpyHostToDevice, s));
         FX_CUDA(cudaMemcpy2DAsync(V, ldv * 8, Vout, n_ld * 8, n * 8, k, cudaMemcpyDeviceToDevice, s));
@@ -399,6 +402,29 @@ extern "C" int fx_kpca_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t 
                                int kernel_id, const double* kparams, int k, int center, double alpha,
                                double eps, const fx_solver_opts* opts, double* V, int64_t ldv,
                                double* lambda, fx_model** model, fx_stats* stats) {
+    if (ctx && !ctx->sub.empty()) {
+        // single-process multi-GPU: one host thread per device runs the rank's share of the fit
+        if (!V) { fx_set_error("kpca_fit: V is NULL"); return -13; }
+        if (!lambda) { fx_set_error("kpca_fit: lambda is NULL"); return -15; }
+        const int G = (int)ctx->sub.size();
+        std::vector<fx_model*> models(G, nullptr);
+        std::vector<fx_stats> sts(G);
+        if (model) *model = nullptr;
+        const int rc = fx_multi_run(ctx, [&](fx_ctx* c, int r) {
+            return kpca_fit_impl(c, X, false, n, d, ldx, kernel_id, kparams, k, center, alpha, eps, opts,
+                                 r == 0 ? V : nullptr, ldv, r == 0 ? lambda : nullptr, model ? &models[r] : nullptr,
+                                 &sts[r]);
+        });
+        if (stats) *stats = sts[0];
+        if ((rc == 0 || rc == FX_ERR_NOT_CONVERGED) && model) {
+            fx_model* m = new fx_model();
+            m->sub = models;
+            *model = m;
+        } else {
+            for (fx_model* m : models) fx_model_free(m);
+        }
+        return rc;
+    }
     return kpca_fit_impl(ctx, X, false, n, d, ldx, kernel_id, kparams, k, center, alpha, eps, opts, V,
                          ldv, lambda, model, stats);
 }
@@ -421,6 +447,7 @@ extern "C" int fx_gram_f64(fx_ctx* ctx, const double* Z, int64_t m, int64_t ldz,
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("fx_gram_f64: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     const bool sym = (Z == nullptr);
     if (sym) { m = n; }
     if (m < 1) { fx_set_error("fx_gram_f64: invalid argument 2 (m < 1)"); return -2; }
@@ -484,6 +511,7 @@ extern "C" int fx_center_f64(fx_ctx* ctx, double* K, int64_t n, int64_t ldk, dou
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("fx_center_f64: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     if (!K) { fx_set_error("fx_center_f64: invalid argument 2 (!K)"); return -2; }
     if (n < 1) { fx_set_error("fx_center_f64: invalid argument 3 (n < 1)"); return -3; }
     if (ldk < n) { fx_set_error("center: ldk < n (DimensionMismatch)"); return -4; }
@@ -524,6 +552,7 @@ extern "C" int fx_symm_f64(fx_ctx* ctx, const double* K, int64_t n, int64_t ldk,
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("fx_symm_f64: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     if (!K) { fx_set_error("fx_symm_f64: invalid argument 2 (!K)"); return -2; }
     if (n < 1) { fx_set_error("fx_symm_f64: invalid argument 3 (n < 1)"); return -3; }
     if (ldk < n) { fx_set_error("fx_symm_f64: invalid argument 4 (ldk < n; DimensionMismatch)"); return -4; }
@@ -577,6 +606,7 @@ extern "C" int fx_center_symm_f64(fx_ctx* ctx, double* K, int64_t n, int64_t ldk
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("fx_center_symm_f64: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     if (!K) { fx_set_error("fx_center_symm_f64: invalid argument 2 (!K)"); return -2; }
     if (n < 1) { fx_set_error("fx_center_symm_f64: invalid argument 3 (n < 1)"); return -3; }
     if (ldk < n) { fx_set_error("fx_center_symm_f64: invalid argument 4 (ldk < n; DimensionMismatch)"); return -4; }
@@ -632,6 +662,7 @@ extern "C" int fx_center_symm_f64(fx_ctx* ctx, double* K, int64_t n, int64_t ldk
 
 extern "C" int fx_syevd_small_f64(fx_ctx* ctx, double* A, int m, int64_t lda, double* w, int* sweeps) {
     if (!ctx) { fx_set_error("fx_syevd_small_f64: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     if (!A) { fx_set_error("fx_syevd_small_f64: invalid argument 2 (!A)"); return -2; }
     if (m < 1 || m > 1024) { fx_set_error("syevd_small: order must be 1..1024"); return -3; }
     if (lda < m) { fx_set_error("syevd_small: lda < m (DimensionMismatch)"); return -4; }

@@ -13,6 +13,34 @@ int transform_impl(fx_ctx* ctx, const fx_model* md, const double* Z, bool on_dev
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("transform: ctx is NULL"); return -1; }
     if (!md) { fx_set_error("transform: model is NULL"); return -2; }
+    if (!ctx->sub.empty()) {
+        // multi-GPU context: the queries are sharded over the devices (kpca.jl:64-68 has no coupling
+        // between queries), every device holds a replica of the model, no collective
+        if (md->sub.size() != ctx->sub.size()) { fx_set_error("transform: the model was not fitted on this multi-GPU context"); return -2; }
+        if (on_dev) { fx_set_error("transform: device-pointer entry points need a single-device context"); return -1; }
+        if (!Z) { fx_set_error("transform_impl: invalid argument 3 (!Z)"); return -3; }
+        if (m < 1) { fx_set_error("transform_impl: invalid argument 4 (m < 1)"); return -4; }
+        if (!out) { fx_set_error("transform_impl: invalid argument 6 (!out)"); return -6; }
+        const int G = (int)ctx->sub.size();
+        std::vector<fx_stats> sts(G);
+        for (auto& x : sts) memset(&x, 0, sizeof(x));
+        const int rc = fx_multi_run(ctx, [&](fx_ctx* c, int r) {
+            const int64_t base = m / G, rem = m % G;
+            const int64_t q0 = r * base + (r < rem ? r : rem), cnt = base + (r < rem ? 1 : 0);
+            if (cnt == 0) return 0;
+            return transform_impl(c, md->sub[r], Z + q0, false, cnt, ldz, out + q0, ldo, &sts[r], variant);
+        });
+        if (stats) {
+            *stats = sts[0];
+            for (int r = 1; r < G; ++r) {
+                if (sts[r].total_ms > stats->total_ms) stats->total_ms = sts[r].total_ms;
+                if (sts[r].transform_ms > stats->transform_ms) stats->transform_ms = sts[r].transform_ms;
+                stats->h2d_bytes += sts[r].h2d_bytes; stats->d2h_bytes += sts[r].d2h_bytes;
+                stats->transform_launches += sts[r].transform_launches; stats->kernel_launches += sts[r].kernel_launches;
+            }
+        }
+        return rc;
+    }
     if (!Z) { fx_set_error("transform_impl: invalid argument 3 (!Z)"); return -3; }
     if (m < 1) { fx_set_error("transform_impl: invalid argument 4 (m < 1)"); return -4; }
     if (ldz < m) { fx_set_error("transform: ldz < m (DimensionMismatch)"); return -5; }
@@ -113,6 +141,22 @@ extern "C" int fx_model_create_f64(fx_ctx* ctx, const double* X, int64_t n, int6
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("fx_model_create_f64: ctx is NULL"); return -1; }
+    if (!ctx->sub.empty()) {
+        // one replica per device
+        if (!model) { fx_set_error("model is NULL"); return -12; }
+        const int G = (int)ctx->sub.size();
+        std::vector<fx_model*> models(G, nullptr);
+        std::vector<fx_stats> sts(G);
+        const int rc = fx_multi_run(ctx, [&](fx_ctx* c, int r) {
+            return fx_model_create_f64(c, X, n, d, ldx, kernel_id, kparams, W, k, ldw, center, &models[r], &sts[r]);
+        });
+        if (stats) *stats = sts[0];
+        if (rc) { for (fx_model* x : models) fx_model_free(x); *model = nullptr; return rc; }
+        fx_model* mm = new fx_model();
+        mm->sub = models;
+        *model = mm;
+        return 0;
+    }
     if (!X) { fx_set_error("fx_model_create_f64: invalid argument 2 (!X)"); return -2; }
     if (n < 1) { fx_set_error("fx_model_create_f64: invalid argument 3 (n < 1)"); return -3; }
     if (d < 1) { fx_set_error("fx_model_create_f64: invalid argument 4 (d < 1)"); return -4; }

@@ -128,6 +128,7 @@ int time_loop(fx_ctx* ctx, int reps, double* ms_out, const std::function<int()>&
 extern "C" int fx_bench_kernel(fx_ctx* ctx, int which, int64_t n, int64_t d, int b, int64_t m,
                                int kernel_id, int reps, double* ms_out) {
     if (!ctx) { fx_set_error("fx_bench_kernel: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     if (reps < 1 || !ms_out) { fx_set_error("fx_bench_kernel: invalid argument 8 (reps < 1 || !ms_out)"); return -8; }
     FX_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;

@@ -15,6 +15,7 @@ typedef int (*pfn_CommDestroy)(ncclComm_p);
 typedef int (*pfn_AllReduce)(const void*, void*, size_t, int, int, ncclComm_p, cudaStream_t);
 typedef int (*pfn_AllGather)(const void*, void*, size_t, int, ncclComm_p, cudaStream_t);
 typedef const char* (*pfn_GetErrorString)(int);
+typedef int (*pfn_Group)(void);
 constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 
 struct NcclApi {
@@ -25,6 +26,7 @@ struct NcclApi {
     pfn_AllReduce AllReduce = nullptr;
     pfn_AllGather AllGather = nullptr;
     pfn_GetErrorString GetErrorString = nullptr;
+    pfn_Group GroupStart = nullptr, GroupEnd = nullptr;
     bool ok = false;
 };
 NcclApi g_nccl;
@@ -44,6 +46,8 @@ void load_nccl() {
     g_nccl.AllReduce = (pfn_AllReduce)dlsym(g_nccl.handle, "ncclAllReduce");
     g_nccl.AllGather = (pfn_AllGather)dlsym(g_nccl.handle, "ncclAllGather");
     g_nccl.GetErrorString = (pfn_GetErrorString)dlsym(g_nccl.handle, "ncclGetErrorString");
+    g_nccl.GroupStart = (pfn_Group)dlsym(g_nccl.handle, "ncclGroupStart");
+    g_nccl.GroupEnd = (pfn_Group)dlsym(g_nccl.handle, "ncclGroupEnd");
     g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce &&
                 g_nccl.AllGather && g_nccl.GetErrorString;
 }
@@ -95,6 +99,28 @@ int fxcomm_create(int rank, int world, const void* id128, FxComm** out) {
         return FX_ERR_NCCL;
     }
     *out = c;
+    return 0;
+}
+
+int fxcomm_create_all(const int* devices, int ndev, FxComm** out) {
+    FX_TRY(need_nccl());
+    if (!g_nccl.GroupStart || !g_nccl.GroupEnd) { fx_set_error("NCCL: ncclGroupStart/End not found"); return FX_ERR_NCCL; }
+    ncclUniqueId_t id;
+    FX_NCCL(g_nccl.GetUniqueId(&id));
+    for (int i = 0; i < ndev; ++i) { out[i] = new FxComm(); out[i]->rank = i; out[i]->world = ndev; }
+    FX_NCCL(g_nccl.GroupStart());
+    int rc = 0;
+    for (int i = 0; i < ndev && !rc; ++i) {
+        if (cudaSetDevice(devices[i]) != cudaSuccess) { rc = -1; break; }
+        rc = g_nccl.CommInitRank(&out[i]->comm, ndev, id, i);
+    }
+    const int re = g_nccl.GroupEnd();
+    if (rc || re) {
+        fx_set_error("ncclCommInitRank (single process, %d devices) failed: %s", ndev,
+                     g_nccl.GetErrorString(rc > 0 ? rc : re));
+        for (int i = 0; i < ndev; ++i) { delete out[i]; out[i] = nullptr; }
+        return FX_ERR_NCCL;
+    }
     return 0;
 }
 

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -41,6 +43,8 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct FxComm;
 int  fxcomm_unique_id(void* id128);
 int  fxcomm_create(int rank, int world, const void* id128, FxComm** out);
+// single process, one communicator per device (ncclGroupStart / ncclCommInitRank / ncclGroupEnd)
+int  fxcomm_create_all(const int* devices, int ndev, FxComm** out);
 void fxcomm_destroy(FxComm* c);
 int  fxcomm_allreduce_sum(FxComm* c, double* buf, size_t count, cudaStream_t s);      // in place
 int  fxcomm_allgather(FxComm* c, const double* send, double* recv, size_t count_per_rank,
@@ -49,8 +53,29 @@ int  fxcomm_allgather(FxComm* c, const double* send, double* recv, size_t count_
 // ------------------------------------------------------------------------------------------
 // context: one GPU, one stream, a grow-only device arena reused across calls
 // ------------------------------------------------------------------------------------------
+// Host-side rendezvous of the rank threads of a single-process multi-GPU context (fx_init_multi).
+struct FxMultiShared {
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0, generation = 0, n = 0;
+    char* arena[16] = {};
+    size_t off[16][2] = {};
+    int ok[16] = {};
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const int gen = generation;
+        if (++arrived == n) { arrived = 0; ++generation; cv.notify_all(); }
+        else cv.wait(lk, [&] { return generation != gen; });
+    }
+};
+
 struct fx_ctx {
     int device = 0, rank = 0, world = 1, sm_count = 148;
+    // Single-process multi-GPU: the PARENT context (fx_init_multi) owns one sub-context per device and
+    // no device state of its own; every entry point fans out to one host thread per sub-context.
+    std::vector<fx_ctx*> sub;
+    fx_ctx* parent = nullptr;
+    FxMultiShared* ms = nullptr;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     // side stream for the small Rayleigh-Ritz problem that runs beside the next K*V pass
@@ -127,6 +152,7 @@ struct FxTimer {
 // fitted model (device resident, replicated on every rank)
 // ------------------------------------------------------------------------------------------
 struct fx_model {
+    std::vector<fx_model*> sub;   // model of a multi-GPU parent context: one replica per device
     int device = 0;
     int64_t n = 0, d = 0, n_ld = 0, d_pad = 0;
     int k = 0, k_pad = 0;

@@ -1,6 +1,12 @@
 // fx_kernels.cuh -- host-side launchers of the hand-written sm_100a kernels.
 #pragma once
+#include <functional>
 #include "fx_common.cuh"
+
+// ---- api_core.cu: single-process multi-GPU fan-out -----------------------------------------------
+int fx_multi_run(fx_ctx* parent, const std::function<int(fx_ctx*, int)>& fn);
+// building blocks and the linear solvers run on one GPU: a multi-GPU parent lends its first device
+static inline fx_ctx* fx_single(fx_ctx* ctx) { return (ctx && !ctx->sub.empty()) ? ctx->sub[0] : ctx; }
 
 // ---- gram.cu ---------------------------------------------------------------------------
 // K[i][j] = map(A_i . B_j) for i in [0, rows_pad), j in [0, ldk); operands are feature-major

@@ -248,11 +248,50 @@ static int klda_dense(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_
     return 0;
 }
 
+static int klda_fit_impl(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx,
+                         int kernel_id, const double* kparams, const int64_t* y, int nclass,
+                         const double* freq, double alpha_b, double eps_b, double alpha_w,
+                         double eps_w, int ncomp, const fx_solver_opts* opts, double* A,
+                         int64_t lda, double* lambda, fx_model** model, fx_stats* stats);
+
 extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx,
                                int kernel_id, const double* kparams, const int64_t* y, int nclass,
                                const double* freq, double alpha_b, double eps_b, double alpha_w,
                                double eps_w, int ncomp, const fx_solver_opts* opts, double* A,
                                int64_t lda, double* lambda, fx_model** model, fx_stats* stats) {
+    if (ctx && ctx->sub.size() == 1) ctx = ctx->sub[0];
+    if (ctx && !ctx->sub.empty()) {
+        // single-process multi-GPU: one host thread per device (see fx_kpca_fit_f64)
+        if (!A) { fx_set_error("fx_klda_fit_f64: invalid argument 17 (!A)"); return -17; }
+        if (!lambda) { fx_set_error("fx_klda_fit_f64: invalid argument 19 (!lambda)"); return -19; }
+        const int G = (int)ctx->sub.size();
+        std::vector<fx_model*> models(G, nullptr);
+        std::vector<fx_stats> sts(G);
+        if (model) *model = nullptr;
+        const int rc = fx_multi_run(ctx, [&](fx_ctx* c, int r) {
+            return klda_fit_impl(c, X, n, d, ldx, kernel_id, kparams, y, nclass, freq, alpha_b, eps_b, alpha_w, eps_w,
+                                 ncomp, opts, r == 0 ? A : nullptr, lda, r == 0 ? lambda : nullptr,
+                                 model ? &models[r] : nullptr, &sts[r]);
+        });
+        if (stats) *stats = sts[0];
+        if (rc == 0 && model) {
+            fx_model* m = new fx_model();
+            m->sub = models;
+            *model = m;
+        } else {
+            for (fx_model* m : models) fx_model_free(m);
+        }
+        return rc;
+    }
+    return klda_fit_impl(ctx, X, n, d, ldx, kernel_id, kparams, y, nclass, freq, alpha_b, eps_b, alpha_w, eps_w, ncomp,
+                         opts, A, lda, lambda, model, stats);
+}
+
+static int klda_fit_impl(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int64_t ldx,
+                         int kernel_id, const double* kparams, const int64_t* y, int nclass,
+                         const double* freq, double alpha_b, double eps_b, double alpha_w,
+                         double eps_w, int ncomp, const fx_solver_opts* opts, double* A,
+                         int64_t lda, double* lambda, fx_model** model, fx_stats* stats) {
     fx_stats local;
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
@@ -290,9 +329,10 @@ extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t 
         return FX_ERR_NOT_POSDEF;
     }
     if (ncomp < 1 || ncomp > (dense ? n : c)) { fx_set_error("klda_fit: ncomp must lie in 1..nclass"); return -15; }
-    if (!A) { fx_set_error("fx_klda_fit_f64: invalid argument 17 (!A)"); return -17; }
+    const bool mute = ctx->parent && ctx->rank != 0;       // in-process rank other than the leader: no host output
+    if (!A && !mute) { fx_set_error("fx_klda_fit_f64: invalid argument 17 (!A)"); return -17; }
     if (lda < n) { fx_set_error("klda_fit: lda < n (DimensionMismatch)"); return -18; }
-    if (!lambda) { fx_set_error("fx_klda_fit_f64: invalid argument 19 (!lambda)"); return -19; }
+    if (!lambda && !mute) { fx_set_error("fx_klda_fit_f64: invalid argument 19 (!lambda)"); return -19; }
     std::vector<double> inv_cnt(c, 0.0), hfreq(freq, freq + c);
     {
         std::vector<int64_t> cnt(c, 0);
@@ -534,10 +574,12 @@ extern "C" int fx_klda_fit_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t 
         FX_CUDA(cudaMemcpyAsync(Aout, Aloc, (size_t)ncp * ld * 8, cudaMemcpyDeviceToDevice, s));
     }
     tm.begin(&st->d2h_ms);
-    FX_CUDA(cudaMemcpy2DAsync(A, lda * 8, Aout, n_ld * 8, n * 8, ncomp, cudaMemcpyDeviceToHost, s));
-    FX_CUDA(cudaMemcpyAsync(lambda, lam, ncomp * 8, cudaMemcpyDeviceToHost, s));
+    if (!mute) {
+        FX_CUDA(cudaMemcpy2DAsync(A, lda * 8, Aout, n_ld * 8, n * 8, ncomp, cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaMemcpyAsync(lambda, lam, ncomp * 8, cudaMemcpyDeviceToHost, s));
+        st->d2h_bytes += n * ncomp * 8 + ncomp * 8;
+    }
     tm.end();
-    st->d2h_bytes += n * ncomp * 8 + ncomp * 8;
     int hbad[8] = {0};
     FX_CUDA(cudaMemcpyAsync(hbad, info, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (model) FX_TRY(fx_model_build(ctx, g, kernel_id, kpv, ncomp, Aout, false, true, model));

@@ -130,6 +130,7 @@ extern "C" int fx_pca_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, in
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("fx_pca_f64: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     if (!X) { fx_set_error("fx_pca_f64: invalid argument 2 (!X)"); return -2; }
     if (n < 2) { fx_set_error("fx_pca_f64: invalid argument 3 (n < 2)"); return -3; }
     if (p < 1 || p > 512) { fx_set_error("pca: p must lie in 1..512"); return -4; }
@@ -191,6 +192,7 @@ extern "C" int fx_project_f64(fx_ctx* ctx, const double* W, int64_t p, int k, in
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("fx_project_f64: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     if (!W) { fx_set_error("fx_project_f64: invalid argument 2 (!W)"); return -2; }
     if (p < 1 || p > 512) { fx_set_error("project: p must lie in 1..512"); return -3; }
     if (k < 1 || k > 512) { fx_set_error("fx_project_f64: invalid argument 4 (k < 1 || k > 512)"); return -4; }
@@ -370,6 +372,7 @@ extern "C" int fx_lda_f64(fx_ctx* ctx, const double* X, int64_t n, int64_t p, in
     fx_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof(*st));
     if (!ctx) { fx_set_error("fx_lda_f64: ctx is NULL"); return -1; }
+    ctx = fx_single(ctx);
     if (!X) { fx_set_error("fx_lda_f64: invalid argument 2 (!X)"); return -2; }
     if (n < 2) { fx_set_error("fx_lda_f64: invalid argument 3 (n < 2)"); return -3; }
     if (p < 1 || p > 512) { fx_set_error("lda: p must lie in 1..512"); return -4; }

@@ -102,6 +102,12 @@ int  fx_init(int device, fx_ctx** out);
  * rank calls fx_init_distributed.  K is sharded by row blocks; X is replicated. */
 int  fx_comm_unique_id(void* id128);
 int  fx_init_distributed(int device, int rank, int world, const void* id128, fx_ctx** out);
+/* Multi-GPU in ONE process: the context drives `ndev` GPUs of this node with one host
+ * thread per device; NCCL communicators and NVLink peer access are set up inside the library, the
+ * caller makes one call per fit / transform with host buffers and never sees ranks.  fit shards K
+ * by row blocks, transform shards the queries; the building blocks and the linear solvers run on
+ * devices[0].  Device-pointer entry points (*_dev_*) and fx_set_stream need a single-device context. */
+int  fx_init_multi(const int* devices, int ndev, fx_ctx** out);
 int  fx_set_stream(fx_ctx* ctx, void* cuda_stream);     /* run on a caller-owned stream    */
 int  fx_ctx_info(const fx_ctx* ctx, int* device, int* rank, int* world, int* sm_count);
 /* 1 if the last collective fit reached every other rank's workspace over NVLink peer mappings

@@ -34,7 +34,20 @@ mutable struct Context
     end
 end
 
-# Multi-GPU: one Julia process per GPU (Distributed / MPI.jl).  Rank 0 draws the communicator id,
+# Multi-GPU from ONE Julia process (the normal way): the library drives the listed devices itself
+# (one host thread per GPU, NCCL and NVLink peer access set up inside); `kpca(X, κ; k=...)` stays a
+# single call.   use_context!(multi_context([0, 1, 2, 3, 4, 5, 6, 7]))
+function multi_context(devices::AbstractVector{<:Integer})
+    devs = Cint.(collect(devices))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:fx_init_multi, libfx), Cint, (Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}), devs, length(devs), r),
+          "fx_init_multi")
+    c = Context(r[])
+    finalizer(x -> ccall((:fx_shutdown, libfx), Cvoid, (Ptr{Cvoid},), x.h), c)
+    c
+end
+
+# Multi-GPU alternative: one Julia process per GPU (Distributed / MPI.jl).  Rank 0 draws the communicator id,
 # the host program ships the 128 bytes to every rank, every rank opens its context and installs it
 # with `use_context!`; the same `kpca(X, κ; k=...)` call on every rank then returns the full (V, Λ).
 function comm_unique_id()

@@ -37,3 +37,52 @@ def test_two_gpu_sharded_fit_without_peer_access():
     NVLink peer access is unavailable); same results."""
     out = _run(2, 29649, {"FXB200_NO_PEER": "1"})
     assert "peer=1" not in out
+
+
+@pytest.mark.parametrize("ndev", [2, 4])
+def test_single_process_multi_gpu_context(ndev):
+    """fx_init_multi: ONE process drives `ndev` GPUs -- one host thread per device
+    inside the library, in-process NCCL communicators, direct peer access.  The caller makes one call
+    per fit / transform with host buffers.  Results: against the oracle, and eigenvalues identical to
+    the one-GPU context of the same process."""
+    import numpy as np
+    import torch
+    import oracle as O
+    import fxb200
+    from fxb200.synth import mix
+    if torch.cuda.device_count() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    ctx = fxb200.Context.multi(list(range(ndev)))
+    one = fxb200.Context(0)
+    assert ctx.world == ndev
+    for (n, d, k) in [(4096, 64, 8), (1500, 20, 4), (1000, 10, 2)]:
+        X, _ = mix(n, d, k + 1, 3.0, 61)
+        kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+        V, L, model, st = fxb200.kpca(X, kern, k=k, ctx=ctx, return_model=True, return_stats=True)
+        V1, L1 = fxb200.kpca(X, kern, k=k, ctx=one)
+        Vo, Lo = O.kpca(X, okern)
+        np.testing.assert_allclose(L, Lo[:k], rtol=1e-10)
+        np.testing.assert_allclose(L, L1, rtol=1e-13)
+        Qa, _ = np.linalg.qr(V)
+        assert np.linalg.norm(Vo[:, :k] - Qa @ (Qa.T @ Vo[:, :k]), 2) < 1e-8
+        Z, _ = mix(1001, d, k + 1, 3.0, 62)
+        T = model.transform(Z)                               # queries sharded over the devices
+        To = O.transform_kpca(X, okern, V, Z)
+        assert np.abs(T - To).max() <= 1e-10 * np.abs(To).max()
+        model.free()
+        print("MULTI_OK ndev=%d n=%d steps=%d peer=%d" % (ndev, n, st["steps"], ctx.peer_access))
+    # KLDA through the same context (iterative path: the dense one is single-GPU)
+    n, d, c = 1500, 32, 5
+    X, y0 = mix(n, d, c, 2.0, 63)
+    y = y0 + 1
+    freq = np.bincount(y0, minlength=c) / n
+    kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+    H_b, H_w, _ = O.lda_matrices(O.kernelmatrix(okern, X), y, c, freq)
+    eps_w = 1e-6 * np.trace(O.scatter_matrices(H_b, 0, 0, H_w, 0, 0)[1]) / n
+    Ao, Lo = O.klda(X, okern, y, c, freq, eps_w=eps_w)
+    A, L = fxb200.klda(X, kern, y, c, freq, eps_w=eps_w, ctx=ctx)
+    np.testing.assert_allclose(L, Lo, rtol=1e-7)
+    # building blocks on a multi-GPU context run on its first device
+    K = fxb200.kernelmatrix(kern, X[:300], ctx=ctx)
+    assert np.abs(K - O.kernelmatrix(okern, X[:300])).max() < 1e-13
+    ctx.close(); one.close()
