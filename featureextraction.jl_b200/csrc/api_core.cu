@@ -42,6 +42,31 @@ int fx_arena_reserve(fx_ctx* ctx, size_t bytes) {
     return 0;
 }
 
+static int peer_stage_alloc(fx_ctx* ctx) {
+    if (!ctx->peer_stage) FX_CUDA(cudaMalloc((void**)&ctx->peer_stage, (size_t)(12 + 12 * fx_ctx::MAX_PEERS) * 8));
+    return 0;
+}
+
+int fx_agree(fx_ctx* ctx, int rc) {
+    if (ctx->world <= 1 || !ctx->comm) return rc;
+    if (peer_stage_alloc(ctx)) return rc ? rc : FX_ERR_OOM;       // cannot even talk: local verdict
+    double* hp = ctx->pinned + 3400;                    // (0..3071: solver / eigenvalue scratch, 3072..3291: peer exchange)
+    hp[0] = rc ? 1.0 : 0.0;
+    cudaStream_t s = ctx->stream;
+    if (cudaMemcpyAsync(ctx->peer_stage, hp, 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return rc ? rc : FX_ERR_CUDA;
+    if (fxcomm_allreduce_sum(ctx->comm, ctx->peer_stage, 1, s)) return rc ? rc : FX_ERR_NCCL;
+    if (cudaMemcpyAsync(hp, ctx->peer_stage, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+        return rc ? rc : FX_ERR_CUDA;
+    if (rc) return rc;
+    if (hp[0] != 0.0) {
+        fx_set_error("another rank failed before the collective section of this call (%d of %d ranks reported an "
+                     "error, e.g. out of device memory); this rank gives up with it", (int)hp[0], ctx->world);
+        return FX_ERR_CUDA;
+    }
+    return 0;
+}
+
 void fx_peer_close_all(fx_ctx* ctx) {
     for (int c = 0; c < fx_ctx::MAX_PEERS; ++c) {
         if (ctx->peer_arena[c]) {
@@ -85,7 +110,7 @@ static int fx_peer_exchange_inproc(fx_ctx* ctx, size_t off0, size_t off1) {
     if (!all_ok) return 0;
     // stream-ordered barrier across the ranks: no rank writes into a peer before that peer is done
     // with its previous use of the buffers
-    if (!ctx->peer_stage) FX_CUDA(cudaMalloc((void**)&ctx->peer_stage, 256));
+    FX_TRY(peer_stage_alloc(ctx));
     FX_CUDA(cudaMemsetAsync(ctx->peer_stage, 0, 8, ctx->stream));
     FX_TRY(fxcomm_allreduce_sum(ctx->comm, ctx->peer_stage, 1, ctx->stream));
     ctx->peer_valid = true;
@@ -101,7 +126,7 @@ int fx_peer_exchange(fx_ctx* ctx, size_t off0, size_t off1) {
     if (disabled) return 0;
     constexpr int W = 12;                                  // doubles per rank in the exchange
     cudaStream_t s = ctx->stream;
-    if (!ctx->peer_stage) FX_CUDA(cudaMalloc((void**)&ctx->peer_stage, (size_t)(W + W * fx_ctx::MAX_PEERS) * 8));
+    FX_TRY(peer_stage_alloc(ctx));
     double* hp = ctx->pinned + 3072;                       // [W] send, then [G][W] received
     cudaIpcMemHandle_t h;
     memset(&h, 0, sizeof(h));

@@ -251,6 +251,10 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     const int64_t launches0 = ctx->launches;
     fx_solver_opts o;
     fx_resolve_opts(opts, k, &o);
+    if (const char* e = getenv("FXB200_BLOCK")) {                  // tuning knob for experiments
+        const int v = atoi(e);
+        if (v >= k && v <= 64 && (!opts || opts->block <= 0)) o.block = (int)round_up(v, 8);
+    }
     const int G = ctx->world;
     const int64_t ld = round_up(ceil_div(n, G), 128), n_ld = ld * G;
     if (!opts || opts->max_blocks <= 1) {
@@ -290,7 +294,7 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     need += fx_align256((size_t)kp * n_ld * 8) + fx_align256((size_t)(kp + 8) * 8) + 4096;
     if (dense) need += 3 * fx_align256((size_t)n * n * 8) + fx_align256((size_t)n_ld * n_ld * 8) + 8192;
     else need += fx_eig_workspace_bytes(ctx, ld, n_ld, k, o) + (grouped ? fx_align256((size_t)kp * ld * 8) : 0);
-    FX_TRY(fx_arena_reserve(ctx, need));
+    FX_TRY(fx_agree(ctx, fx_arena_reserve(ctx, need)));          // all ranks or none enter the collectives
     fx_arena_reset(ctx);
 
     TotalTimer tot;

@@ -131,6 +131,10 @@ static inline void fx_arena_reset(fx_ctx* ctx) { ctx->arena_off = 0; }
 // Falls back to peer_valid == false (identically on every rank) if IPC is unavailable or
 // FXB200_NO_PEER=1.
 int fx_peer_exchange(fx_ctx* ctx, size_t off0, size_t off1);
+// Collective (no-op for one rank): every rank passes its local status before a section full of
+// collectives; if ANY rank failed (e.g. its workspace allocation), all ranks return an error instead
+// of some of them blocking in NCCL forever.  Returns rc if non-zero, else FX_ERR_CUDA when a peer failed.
+int fx_agree(fx_ctx* ctx, int rc);
 void fx_peer_close_all(fx_ctx* ctx);
 static inline size_t fx_align256(size_t b) { return (b + 255) & ~size_t(255); }
 

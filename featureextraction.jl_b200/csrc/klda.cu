@@ -367,7 +367,7 @@ static int klda_fit_impl(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int
     size_t need = fx_gramstage_bytes(ld, n_ld, d_pad, false) + 12 * blk + fx_align256((size_t)G * cp * ld * 8) +
                   fx_align256((size_t)splits * cp * ld * 8) + fx_align256(tnscr * 8) + fx_align256((size_t)n_ld * 4) +
                   fx_align256((size_t)ld * 8) + fx_align256((size_t)ncp * n_ld * 8) + 40 * fx_align256(64 * 64 * 8) + 65536;
-    FX_TRY(fx_arena_reserve(ctx, need));
+    FX_TRY(fx_agree(ctx, fx_arena_reserve(ctx, need)));          // all ranks or none enter the collectives
     fx_arena_reset(ctx);
     cudaStream_t s = ctx->stream;
     cudaEvent_t e0, e1;

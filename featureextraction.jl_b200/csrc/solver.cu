@@ -325,6 +325,9 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
         res_prev2 = res_prev;
         res_prev = maxres;
         converged = maxres <= o.tol;
+        static const bool trace = []() { const char* e = getenv("FXB200_TRACE_SOLVER"); return e && e[0] == '1'; }();
+        if (trace && ctx->rank == 0)
+            fprintf(stderr, "[fxb200 solver] step %d m=%d nlock=%d max rel residual %.3e\n", steps, m, a.nlock, maxres);
         if (converged || steps >= o.max_steps) {
             if (pending) wasted = 1;
             break;
