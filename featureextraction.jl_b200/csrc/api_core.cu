@@ -49,6 +49,24 @@ static int peer_stage_alloc(fx_ctx* ctx) {
 
 int fx_agree(fx_ctx* ctx, int rc) {
     if (ctx->world <= 1 || !ctx->comm) return rc;
+    if (ctx->parent) {
+        // rank threads of one process: agree on the host (also keeps every cudaMalloc of the workspace
+        // phase ahead of the first collective: with peer access enabled an allocation synchronises
+        // with the peer devices and must not meet a rank that already spins inside an NCCL kernel)
+        FxMultiShared* ms = ctx->parent->ms;
+        ms->ok[ctx->rank] = rc ? 0 : 1;
+        ms->barrier();
+        int failed = 0;
+        for (int c = 0; c < ctx->world; ++c) failed += ms->ok[c] ? 0 : 1;
+        ms->barrier();
+        if (rc) return rc;
+        if (failed) {
+            fx_set_error("another device of this multi-GPU context failed before the collective section of this call "
+                         "(%d of %d, e.g. out of device memory)", failed, ctx->world);
+            return FX_ERR_CUDA;
+        }
+        return 0;
+    }
     if (peer_stage_alloc(ctx)) return rc ? rc : FX_ERR_OOM;       // cannot even talk: local verdict
     double* hp = ctx->pinned + 3400;                    // (0..3071: solver / eigenvalue scratch, 3072..3291: peer exchange)
     hp[0] = rc ? 1.0 : 0.0;
@@ -270,6 +288,7 @@ static int ctx_common_init(int device, fx_ctx** out) {
     FX_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->pinned_cap = 4096;
     FX_CUDA(cudaMallocHost((void**)&c->pinned, c->pinned_cap * sizeof(double)));
+    FX_TRY(peer_stage_alloc(c));                            // never allocate between collectives
     *out = c;
     return 0;
 }

@@ -395,7 +395,14 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
         st->d2h_bytes += n * k * 8 + k * 8;
     }
     tm.end();
-    if (model) FX_TRY(fx_model_build(ctx, g, kernel_id, kpv, k, Vout, center != 0, false, model));
+    if (model) {
+        if (ctx->parent) {
+            // in-process ranks: nobody allocates (the model) while a peer may still be inside a collective
+            FX_CUDA(cudaStreamSynchronize(s));
+            ctx->parent->ms->barrier();
+        }
+        FX_TRY(fx_model_build(ctx, g, kernel_id, kpv, k, Vout, center != 0, false, model));
+    }
     FX_TRY(tot.stop(ctx, &st->total_ms));
     tm.resolve();
     st->kernel_launches = ctx->launches - launches0;

@@ -582,7 +582,13 @@ static int klda_fit_impl(fx_ctx* ctx, const double* X, int64_t n, int64_t d, int
     tm.end();
     int hbad[8] = {0};
     FX_CUDA(cudaMemcpyAsync(hbad, info, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (model) FX_TRY(fx_model_build(ctx, g, kernel_id, kpv, ncomp, Aout, false, true, model));
+    if (model) {
+        if (ctx->parent) {
+            FX_CUDA(cudaStreamSynchronize(s));
+            ctx->parent->ms->barrier();
+        }
+        FX_TRY(fx_model_build(ctx, g, kernel_id, kpv, ncomp, Aout, false, true, model));
+    }
     FX_CUDA(cudaEventRecord(e1, s));
     FX_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
