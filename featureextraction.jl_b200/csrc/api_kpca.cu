@@ -276,12 +276,17 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
     if (rows_valid > ld) rows_valid = ld;
     const int64_t d_pad = round_up(d, 16);
     const int kp = (int)round_up(k, 8);
-    // dense Jacobi for tiny problems; k > 64 beyond that: groups of 64 with locking (below)
-    const bool dense = (n <= 256) || (n < 8 * (int64_t)o.block) || (k > 64 && n <= 1024);
+    // Dense paths (all n pairs available, like the reference's dsyevd, common.jl:161-165): two-sided
+    // Jacobi in one CTA for n <= 1024; one-sided (Hestenes) Jacobi over all SMs for 1024 < n <= 8192
+    // when many components are wanted (k > 1024 or k > n/8).  Otherwise the block Krylov solver: one
+    // group for k <= 64, groups of 48 with locking above that.
+    const bool dense_small = (n <= 256) || (n < 8 * (int64_t)o.block) || (k > 64 && n <= 1024);
+    const bool dense_big = !dense_small && n <= 8192 && (k > 1024 || 8 * (int64_t)k > n) && G == 1;
+    const bool dense = dense_small || dense_big;
     const bool grouped = !dense && k > 64;
     if (grouped && k > 1024) {
-        fx_set_error("kpca_fit: k=%d > 1024 components for n > 1024 is not supported (the reference's all-n "
-                     "request, common.jl:164, is served for n <= 1024)", k);
+        fx_set_error("kpca_fit: k=%d > 1024 components is supported up to n = 8192 on one GPU (dense path); "
+                     "for larger n the solver returns at most 1024 leading pairs", k);
         return -8;
     }
     if (!dense) {
@@ -292,7 +297,7 @@ static int kpca_fit_impl(fx_ctx* ctx, const double* X, bool on_dev, int64_t n, i
 
     size_t need = fx_gramstage_bytes(ld, n_ld, d_pad, center != 0);
     need += fx_align256((size_t)kp * n_ld * 8) + fx_align256((size_t)(kp + 8) * 8) + 4096;
-    if (dense) need += 3 * fx_align256((size_t)n * n * 8) + fx_align256((size_t)n_ld * n_ld * 8) + 8192;
+    if (dense) need += 3 * fx_align256((size_t)n_ld * n * 8) + fx_align256((size_t)n_ld * n_ld * 8) + 65536;
     else need += fx_eig_workspace_bytes(ctx, ld, n_ld, k, o) + (grouped ? fx_align256((size_t)kp * ld * 8) : 0);
     FX_TRY(fx_agree(ctx, fx_arena_reserve(ctx, need)));          // all ranks or none enter the collectives
     fx_arena_reset(ctx);

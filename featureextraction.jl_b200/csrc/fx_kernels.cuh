@@ -100,6 +100,10 @@ int fx_launch_jacobi(fx_ctx* ctx, double* A, int lda, int m, double* Vout, int l
 int fx_launch_chol_factors(fx_ctx* ctx, const double* G, int ldg, int b, double thr, double* M, double* Cfac,
                            int* need_svqb, int* ndef);
 size_t fx_jacobi_work_doubles(int m);
+// One-sided (Hestenes) Jacobi: dense full-spectrum eigensolver for 1024 < n <= 8192 (smalldense.cu)
+int fx_hestenes_eig(fx_ctx* ctx, double* A, int64_t ld, int n, int k, double* Vwork, double* lamwork,
+                    int* rankwork, unsigned long long* flag, double* Vout, int64_t ldo, double* theta,
+                    int info_host[2]);
 int fx_launch_hash_fill(fx_ctx* ctx, double* W, int64_t ld, int64_t rows_valid, int64_t row0,
                         int cols, uint64_t seed);
 // SVQB helpers (single CTA)

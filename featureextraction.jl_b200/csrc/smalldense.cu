@@ -345,7 +345,131 @@ __global__ void colsums_kernel(const double* W, long ld, long n, int k, double* 
     if (threadIdx.x == 0) { sums[c] = s; sums[k + c] = a; }
 }
 
+// ---- one-sided (Hestenes) Jacobi for the dense full-spectrum path at 1024 < n <= 8192 --------------------
+// G = A V is kept with mutually orthogonal columns in the limit: for symmetric A the column norms are
+// |lambda_j| and the columns of V the eigenvectors.  One CTA per column pair of a round-robin round
+// (n/2 disjoint pairs: perfectly parallel), three dot products, one plane rotation of the two columns
+// of G and of V.  Memory-bound O(n^3): ~10 sweeps x 32 n^3 bytes.
+__global__ void __launch_bounds__(256) hestenes_round_kernel(double* __restrict__ G, double* __restrict__ V, long ld,
+                                                             int n, int np, int rnd, double floor2,
+                                                             unsigned long long* __restrict__ offmax) {
+    __shared__ double red[33];
+    int p, q;
+    rr_pair(rnd, blockIdx.x, np, p, q);
+    if (q >= n) return;                                          // the bye of an odd n
+    double* gp = G + (long)p * ld; double* gq = G + (long)q * ld;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const double x = gp[r], y = gq[r];
+        a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c);
+    }
+    a = block_sum(a, red); b = block_sum(b, red); c = block_sum(c, red);
+    const double ab = sqrt(a) * sqrt(b);
+    // converged pair: relatively orthogonal, or both columns at the noise floor of the matrix
+    if (fabs(c) <= 1e-15 * ab || fabs(c) <= floor2) return;
+    if (threadIdx.x == 0) atomicMax(offmax, (unsigned long long)__double_as_longlong(fabs(c) / ab));
+    const double zeta = (b - a) / (2.0 * c);
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+    const double cs = rsqrt(fma(t, t, 1.0)), sn = cs * t;
+    double* vp = V + (long)p * ld; double* vq = V + (long)q * ld;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const double x = gp[r], y = gq[r];
+        gp[r] = cs * x - sn * y; gq[r] = sn * x + cs * y;
+        const double u = vp[r], w = vq[r];
+        vp[r] = cs * u - sn * w; vq[r] = sn * u + cs * w;
+    }
+}
+// lam[j] = sign(v_j . g_j) |g_j|  (Rayleigh quotient of the unit vector v_j), one CTA per column
+__global__ void __launch_bounds__(256) hestenes_values_kernel(const double* __restrict__ G, const double* __restrict__ V,
+                                                              long ld, int n, double* __restrict__ lam) {
+    __shared__ double red[33];
+    const int j = blockIdx.x;
+    double a = 0.0, c = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const double x = G[(long)j * ld + r];
+        a = fma(x, x, a); c = fma(x, V[(long)j * ld + r], c);
+    }
+    a = block_sum(a, red); c = block_sum(c, red);
+    if (threadIdx.x == 0) lam[j] = (c < 0.0 ? -1.0 : 1.0) * sqrt(a);
+}
+// descending rank of every eigenvalue (stable), one thread per value
+__global__ void rank_desc_kernel(const double* __restrict__ lam, int n, int* __restrict__ rank) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double di = lam[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) { const double dj = lam[j]; r += (dj > di) || (dj == di && j < i); }
+    rank[i] = r;
+}
+// Vout[:, rank[j]] = V[:, j] for rank[j] < k; theta[rank[j]] = lam[j]
+__global__ void scatter_sorted_kernel(const double* __restrict__ V, long ldv, const double* __restrict__ lam,
+                                      const int* __restrict__ rank, int n, int k, double* __restrict__ Vout, long ldo,
+                                      double* __restrict__ theta) {
+    const int j = blockIdx.x, d = rank[j];
+    if (d >= k) return;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) Vout[(long)d * ldo + r] = V[(long)j * ldv + r];
+    if (threadIdx.x == 0) theta[d] = lam[j];
+}
+__global__ void identity_kernel(double* V, long ld, int n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i < ld) V[(long)j * ld + i] = (i == j && i < n) ? 1.0 : 0.0;
+}
+__global__ void __launch_bounds__(1024) max_colnorm2_kernel(const double* __restrict__ G, long ld, int n, double* out) {
+    __shared__ double red[33];
+    double m = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double a = 0.0;
+        for (int r = threadIdx.x; r < n; r += blockDim.x) { const double x = G[(long)j * ld + r]; a = fma(x, x, a); }
+        a = block_sum(a, red);
+        m = fmax(m, a);
+    }
+    if (threadIdx.x == 0) *out = m;
+}
+
 }  // namespace
+
+// Dense symmetric eigendecomposition by one-sided Jacobi, all on the device: A (n x n symmetric,
+// column-major with leading dimension ld >= n; DESTROYED) -> the k leading (largest algebraic)
+// eigenvalues in theta and eigenvectors in Vout (leading dimension ldo).  Vwork: ld x n scratch,
+// lamwork: n, rankwork: n ints, flag: 8 bytes.  info_host[0] = sweeps, [1] = converged.
+int fx_hestenes_eig(fx_ctx* ctx, double* A, int64_t ld, int n, int k, double* Vwork, double* lamwork,
+                    int* rankwork, unsigned long long* flag, double* Vout, int64_t ldo, double* theta,
+                    int info_host[2]) {
+    cudaStream_t s = ctx->stream;
+    const int np = n + (n & 1);
+    dim3 gi((unsigned)ceil_div(ld, 256), (unsigned)n);
+    identity_kernel<<<gi, 256, 0, s>>>(Vwork, ld, n);
+    max_colnorm2_kernel<<<1, 1024, 0, s>>>(A, ld, n, lamwork);
+    ctx->launches += 2;
+    FX_LAUNCH_CHECK();
+    double scale2 = 0.0;
+    FX_CUDA(cudaMemcpyAsync(&scale2, lamwork, 8, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    const double floor2 = 1e-26 * scale2;                        // (1e-13 |lambda_1|)^2
+    int sweeps = 0, conv = 0;
+    for (; sweeps < 40 && !conv; ++sweeps) {
+        FX_CUDA(cudaMemsetAsync(flag, 0, 8, s));
+        for (int rnd = 0; rnd < np - 1; ++rnd) {
+            hestenes_round_kernel<<<np / 2, 256, 0, s>>>(A, Vwork, ld, n, np, rnd, floor2, flag);
+            ctx->launches++;
+        }
+        FX_LAUNCH_CHECK();
+        unsigned long long bits = 0;
+        FX_CUDA(cudaMemcpyAsync(&bits, flag, 8, cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaStreamSynchronize(s));
+        double off;
+        memcpy(&off, &bits, 8);
+        conv = off <= 1e-14;                                     // a sweep whose largest rotation was at rounding level
+    }
+    hestenes_values_kernel<<<n, 256, 0, s>>>(A, Vwork, ld, n, lamwork);
+    rank_desc_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(lamwork, n, rankwork);
+    scatter_sorted_kernel<<<n, 256, 0, s>>>(Vwork, ld, lamwork, rankwork, n, k, Vout, ldo, theta);
+    ctx->launches += 3;
+    FX_LAUNCH_CHECK();
+    info_host[0] = sweeps; info_host[1] = conv;
+    return 0;
+}
 
 size_t fx_jacobi_work_doubles(int m) { return (size_t)m * m; }
 

@@ -379,6 +379,24 @@ int fx_eig_dense(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
     const int64_t n = a.n, ld = a.ld, n_ld = a.n_ld;
     const int k = a.k, kp = (int)round_up(k, 8);
     cudaStream_t s = ctx->stream;
+    if (n > 1024) {
+        // 1024 < n <= 8192, many components: one-sided Jacobi (one GPU; K is destroyed)
+        if (ctx->world > 1) { fx_set_error("dense full-spectrum path (k > 1024 or k > n/8) needs a single-GPU context"); return -1; }
+        double* Vw = (double*)fx_arena_alloc(ctx, (size_t)n_ld * n * 8);
+        double* lw = (double*)fx_arena_alloc(ctx, (size_t)(n + 8) * 8);
+        int* rw = (int*)fx_arena_alloc(ctx, (size_t)n * 4);
+        unsigned long long* flag = (unsigned long long*)fx_arena_alloc(ctx, 256);
+        if (!Vw || !lw || !rw || !flag) { fx_set_error("internal: arena too small for the dense path"); return FX_ERR_OOM; }
+        FX_CUDA(cudaMemsetAsync(a.Vout, 0, (size_t)kp * n_ld * 8, s));
+        FX_CUDA(cudaMemsetAsync(a.theta, 0, (size_t)kp * 8, s));
+        int hi[2] = {0, 0};
+        tm.begin(&st->rr_ms);
+        FX_TRY(fx_hestenes_eig(ctx, (double*)a.K, a.ldk, (int)n, k, Vw, lw, rw, flag, a.Vout, n_ld, a.theta, hi));
+        tm.end();
+        st->dense_path = 1; st->steps = hi[0]; st->converged = hi[1]; st->block = 0;
+        if (!hi[1]) { fx_set_error("dense one-sided Jacobi did not converge in %d sweeps", hi[0]); return FX_ERR_NOT_CONVERGED; }
+        return 0;
+    }
     double* Kfull = (double*)a.K;
     if (ctx->world > 1) {
         Kfull = (double*)fx_arena_alloc(ctx, (size_t)n_ld * n_ld * 8);

@@ -372,6 +372,25 @@ def test_kpca_more_than_64_components(gpu_ctx, n, d, k, gs):
     model.free()
 
 
+@pytest.mark.parametrize("n,d,k", [(2048, 16, None), (1300, 5, 1300), (2500, 32, 600)])
+def test_kpca_full_spectrum_dense_path(gpu_ctx, n, d, k):
+    """The reference's bare call kpca(X, kernel) returns ALL n pairs (common.jl:164).  For
+    1024 < n <= 8192 that is served by the one-sided (Hestenes) Jacobi solver over all SMs: every
+    eigenvalue against dsyevd, orthonormal V, K~ V = V diag(lambda)."""
+    X, _ = mix(n, d, 6, 3.0, 94)
+    kern, okern = fxb200.GaussianKernel(1.0 / d), O.GaussianKernel(1.0 / d)
+    V, L, st = fxb200.kpca(X, kern, k=k, ctx=gpu_ctx, return_stats=True)
+    kk = n if k is None else k
+    Vo, Lo = O.kpca(X, okern)
+    assert st["dense_path"] == 1 and st["converged"] == 1 and V.shape == (n, kk)
+    assert np.abs(L - Lo[:kk]).max() <= 1e-10 * Lo[0]
+    assert np.abs(V.T @ V - np.eye(kk)).max() < 1e-10
+    Kc, _, _ = O.centerkernelmatrix(O.kernelmatrix(okern, X))
+    R = Kc @ V - V * (L * (n - 1))[None, :]
+    assert np.linalg.norm(R, axis=0).max() <= 1e-10 * Lo[0] * (n - 1)
+    assert sin_angle(V[:, :5], Vo[:, :5]) < 1e-8
+
+
 def test_kpca_degenerate_inputs(gpu_ctx):
     """Duplicate observations (rank-deficient K) and constant data (K~ = 0): eigenvalues must
     match the dense reference path; any orthonormal basis is acceptable for a zero spectrum."""
