@@ -286,7 +286,8 @@ static int ctx_common_init(int device, fx_ctx** out) {
     }
     FX_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     FX_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    c->pinned_cap = 4096;
+    FX_CUDA(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
+    c->pinned_cap = 16384;      // 0..4095 solver scalars / peer exchange / agree flag, 8192.. small matrices (klda.cu)
     FX_CUDA(cudaMallocHost((void**)&c->pinned, c->pinned_cap * sizeof(double)));
     FX_TRY(peer_stage_alloc(c));                            // never allocate between collectives
     *out = c;
@@ -415,6 +416,7 @@ extern "C" void fx_shutdown(fx_ctx* ctx) {
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->comm) fxcomm_destroy(ctx->comm);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->arena) cudaFree(ctx->arena);

@@ -80,7 +80,7 @@ struct fx_ctx {
     bool own_stream = true;
     // side stream for the small Rayleigh-Ritz problem that runs beside the next K*V pass
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     FxComm* comm = nullptr;
     // arena
     char* arena = nullptr;

@@ -256,8 +256,11 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
     // residual history says step s probably converges, the solver does not run ahead, so the
     // speculative pass is wasted at most when the prediction fails.
     static const bool overlap_off = []() { const char* e = getenv("FXB200_NO_OVERLAP"); return e && e[0] == '1'; }();
+    static const bool lag_off = []() { const char* e = getenv("FXB200_NO_LAG"); return e && e[0] == '1'; }();
     bool pending = false;                               // W = K*Qn for this step is already in Wa
-    int wasted = 0;
+    int wasted = 0, last_read = 0;
+    cudaEvent_t ev_rr[2] = {ctx->ev_join, ctx->ev_join2};
+    const int hp_off[2] = {0, 1024};                    // pinned slots of even / odd steps
 
     while (true) {
         double* Qn = w.Q + (size_t)m * ld;
@@ -277,57 +280,84 @@ int fx_eig_topk(fx_ctx* ctx, const EigArgs& a, FxTimer& tm, fx_stats* st) {
         // 7. re-projection of the normalised block + second orthonormalisation -> next block in place
         FX_TRY(reproject_and_orthonormalise(ctx, w, mq, w.Wb, w.Q + (size_t)mq * ld, ld, w.H2, w.M2, w.C2, variant,
                                             tm, st));
-        FX_TRY(fx_launch_small_matmul(ctx, w.C2, w.C1, b, w.C));
         m = mq;
-        // 8. Rayleigh-Ritz on the side stream
+        // 8. Rayleigh-Ritz on the side stream.  The main stream first waits until the PREVIOUS
+        // step's Rayleigh-Ritz has released Tw / C (normally long finished), snapshots T and the
+        // residual factor C for this one, and forks.
+        const int par = steps & 1;
+        double* hp = pinned + hp_off[par];
+        if (steps > 1) FX_CUDA(cudaStreamWaitEvent(s, ev_rr[par ^ 1], 0));
+        FX_TRY(fx_launch_copy2d(ctx, w.T, mt, w.Tw, mt, m, m));
+        FX_TRY(fx_launch_small_matmul(ctx, w.C2, w.C1, b, w.C));
         FX_CUDA(cudaEventRecord(ctx->ev_fork, s));
         FX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
         {
             cudaStream_t keep = ctx->stream;
             ctx->stream = ctx->side;                    // the launchers below use ctx->stream
             tm.begin(&st->rr_ms);
-            int rc = fx_launch_copy2d(ctx, w.T, mt, w.Tw, mt, m, m);
-            if (!rc) rc = fx_launch_jacobi(ctx, w.Tw, mt, m, w.S, mt, w.theta, w.Jw, w.info);
+            int rc = fx_launch_jacobi(ctx, w.Tw, mt, m, w.S, mt, w.theta, w.Jw, w.info);
             if (!rc) rc = fx_launch_ritz_residuals(ctx, w.C, b, w.S, mt, m, k, w.res);
             tm.end();
             ctx->stream = keep;
             FX_TRY(rc);
         }
-        FX_CUDA(cudaMemcpyAsync(pinned, w.res, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->side));
-        FX_CUDA(cudaMemcpyAsync(pinned + 64, w.theta, sizeof(double), cudaMemcpyDeviceToHost, ctx->side));
-        FX_CUDA(cudaMemcpyAsync(pinned + 72, w.info, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->side));
-        FX_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
-        // run ahead with the next K*V pass unless this step is expected to converge
-        bool likely_done = false;
+        FX_CUDA(cudaMemcpyAsync(hp, w.res, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->side));
+        FX_CUDA(cudaMemcpyAsync(hp + 64, w.theta, sizeof(double), cudaMemcpyDeviceToHost, ctx->side));
+        FX_CUDA(cudaMemcpyAsync(hp + 72, w.info, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->side));
+        FX_CUDA(cudaEventRecord(ev_rr[par], ctx->side));
+        auto read_step = [&](int step) -> int {          // host join on the Rayleigh-Ritz of `step`
+            const double* h = pinned + hp_off[step & 1];
+            FX_CUDA(cudaEventSynchronize(ev_rr[step & 1]));
+            const double scale = a.scale_ref > 0.0 ? a.scale_ref : (fabs(h[64]) > 1e-300 ? fabs(h[64]) : 1e-300);
+            double mr = 0.0;
+            for (int i = 0; i < k; ++i) {
+                if (!(h[i] == h[i])) {
+                    fx_set_error("eigensolver: non-finite Ritz residual at step %d", step);
+                    return FX_ERR_NOT_CONVERGED;
+                }
+                if (h[i] > mr) mr = h[i];
+            }
+            maxres = mr / scale;
+            res_prev2 = res_prev;
+            res_prev = maxres;
+            last_read = step;
+            static const bool trace = []() { const char* e = getenv("FXB200_TRACE_SOLVER"); return e && e[0] == '1'; }();
+            if (trace && ctx->rank == 0)
+                fprintf(stderr, "[fxb200 solver] step %d m=%d nlock=%d max rel residual %.3e%s\n", step,
+                        m - (steps - step) * b, a.nlock, maxres, step < steps ? " (read one step late)" : "");
+            return 0;
+        };
+        // The host reads the residuals of the PREVIOUS step here (its Rayleigh-Ritz was queued a
+        // whole step ago, so this join does not idle the GPU) and needs THIS step's Ritz pairs now
+        // only when the step is expected to converge (residual history), a thick restart follows,
+        // or the pass budget is spent.  Otherwise it queues the next step at once: no per-step
+        // host join, the Rayleigh-Ritz chain hides behind the main stream.
+        converged = false;
+        if (last_read < steps - 1) {
+            FX_TRY(read_step(steps - 1));
+            if (maxres <= o.tol) converged = true;       // a step earlier than predicted
+        }
+        bool likely_done = converged;
         if (res_prev >= 0.0 && res_prev2 > 0.0) {
             double ratio = res_prev / res_prev2;
             if (ratio > 1.0) ratio = 1.0;
-            likely_done = res_prev * ratio <= 100.0 * o.tol;
+            if (res_prev * ratio <= 100.0 * o.tol) likely_done = true;
         }
-        if (!overlap_off && variant == 0 && steps < o.max_steps && !likely_done) {
+        const bool run_ahead = !overlap_off && variant == 0 && steps < o.max_steps && !likely_done;
+        const bool need_now = !run_ahead || m + b > w.mcap || lag_off;
+        if (run_ahead) {
             FX_TRY(kv_pass(w.Q + (size_t)m * ld, false));
             pending = true;
         }
-        FX_CUDA(cudaEventSynchronize(ctx->ev_join));
-        FX_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));      // T, S, theta are free for the main stream again
-        const double scale = a.scale_ref > 0.0 ? a.scale_ref : (fabs(pinned[64]) > 1e-300 ? fabs(pinned[64]) : 1e-300);
-        maxres = 0.0;
-        bool finite = true;
-        for (int i = 0; i < k; ++i) {
-            if (!(pinned[i] == pinned[i])) finite = false;
-            if (pinned[i] > maxres) maxres = pinned[i];
+        if (need_now) {
+            // (when the previous step already converged this step's pairs are taken all the same:
+            // they span a larger Krylov space, and S / theta of the earlier step are overwritten)
+            const bool was = converged;
+            FX_TRY(read_step(steps));
+            converged = was || maxres <= o.tol;
         }
-        maxres /= scale;
-        if (!finite) {
-            fx_set_error("eigensolver: non-finite Ritz residual at step %d", steps);
-            return FX_ERR_NOT_CONVERGED;
-        }
-        res_prev2 = res_prev;
-        res_prev = maxres;
-        converged = maxres <= o.tol;
-        static const bool trace = []() { const char* e = getenv("FXB200_TRACE_SOLVER"); return e && e[0] == '1'; }();
-        if (trace && ctx->rank == 0)
-            fprintf(stderr, "[fxb200 solver] step %d m=%d nlock=%d max rel residual %.3e\n", steps, m, a.nlock, maxres);
+        if (last_read == steps)
+            FX_CUDA(cudaStreamWaitEvent(s, ev_rr[par], 0));    // S, theta are final for the main stream
         if (converged || steps >= o.max_steps) {
             if (pending) wasted = 1;
             break;
