@@ -372,7 +372,7 @@ def test_kpca_more_than_64_components(gpu_ctx, n, d, k, gs):
     model.free()
 
 
-@pytest.mark.parametrize("n,d,k", [(2048, 16, None), (1300, 5, 1300), (2500, 32, 600)])
+@pytest.mark.parametrize("n,d,k", [(2048, 16, None), (1300, 5, 1300), (2500, 32, 600), (4096, 32, None)])
 def test_kpca_full_spectrum_dense_path(gpu_ctx, n, d, k):
     """The reference's bare call kpca(X, kernel) returns ALL n pairs (common.jl:164).  For
     1024 < n <= 8192 that is served by the one-sided (Hestenes) Jacobi solver over all SMs: every
