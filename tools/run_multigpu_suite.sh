@@ -19,6 +19,7 @@ nvidia-smi --query-gpu=index,name,clocks.max.sm --format=csv,noheader | head -8
 # distributed parity tests (torchrun worlds 2..4, FXB200_NO_PEER, single-process multi-GPU context)
 timeout 1500 python -m pytest tests/test_gpu_distributed.py -m gpu -q -x -s 2>&1 | tail -30 > $OUT/${TAG}_dist_tests.log
 tail -5 $OUT/${TAG}_dist_tests.log
+run 1 headline --steps 8 --warmup 3 --no-cpu-baseline --transform-m 0
 for g in 2 4 8; do
   [ $g -le $N ] || continue
   run $g headline --steps 8 --warmup 3 --no-cpu-baseline
@@ -26,3 +27,8 @@ for g in 2 4 8; do
 done
 run $N C4 --config C4 --steps 2 --warmup 1
 run $N C5 --config C5 --steps 3 --warmup 2 --no-cpu-baseline
+if [ "$N" = "8" ]; then   # A/B of the solver's latency hiding at 8 GPUs
+  FXB200_NO_LAG=1 run 8 headline_nolag --steps 8 --warmup 3 --no-cpu-baseline --transform-m 0
+  FXB200_MAX_BLOCKS=5 run 8 headline_mb5 --steps 8 --warmup 3 --no-cpu-baseline --transform-m 0
+  FXB200_MAX_BLOCKS=3 run 8 headline_mb3 --steps 8 --warmup 3 --no-cpu-baseline --transform-m 0
+fi
