@@ -42,6 +42,22 @@ int fx_arena_reserve(fx_ctx* ctx, size_t bytes) {
     return 0;
 }
 
+// Cross-rank symmetric Gram (every off-diagonal super-tile computed once, its transpose stored into the
+// owner's K over NVLink from inside the kernel): OPT-IN since round 2 (FXB200_PEER_SYM=1).  With the
+// remote stores in flight a fit occasionally comes out with one 64 x 8 sub-block of K off (about 1 fit in
+// 50 on four GPUs, every second fit on eight; bit-identical to the one-GPU result otherwise): eigenvalues
+// then differ in the 7th digit, far outside the 1e-10 parity bar.  The rank-local schedule (each rank
+// computes its whole row block, symmetric only inside its diagonal block) was bit-reproducible in 600 fits
+// of the same experiment (profiles/r02_peer_sym_investigation.md), so it is the default.
+static bool fx_peer_sym_enabled() {
+    static const bool on = []() {
+        const char* e = getenv("FXB200_PEER_SYM");
+        const char* off = getenv("FXB200_NO_PEER");
+        return e && e[0] == '1' && !(off && off[0] == '1');
+    }();
+    return on;
+}
+
 static int peer_stage_alloc(fx_ctx* ctx) {
     if (!ctx->peer_stage) FX_CUDA(cudaMalloc((void**)&ctx->peer_stage, (size_t)(12 + 12 * fx_ctx::MAX_PEERS) * 8));
     return 0;
@@ -104,7 +120,7 @@ static int fx_peer_exchange_inproc(fx_ctx* ctx, size_t off0, size_t off1) {
     ctx->peer_valid = false;
     const int G = ctx->world, r = ctx->rank;
     FxMultiShared* ms = ctx->parent->ms;
-    static const bool disabled = []() { const char* e = getenv("FXB200_NO_PEER"); return e && e[0] == '1'; }();
+    const bool disabled = !fx_peer_sym_enabled();
     int ok = (!disabled && G <= fx_ctx::MAX_PEERS && ctx->arena) ? 1 : 0;
     for (int c = 0; c < G && ok; ++c) {
         if (c == r) continue;
@@ -140,8 +156,7 @@ int fx_peer_exchange(fx_ctx* ctx, size_t off0, size_t off1) {
     ctx->peer_valid = false;
     const int G = ctx->world;
     if (G <= 1 || G > fx_ctx::MAX_PEERS || !ctx->comm || ctx->peer_failed) return 0;
-    static const bool disabled = []() { const char* e = getenv("FXB200_NO_PEER"); return e && e[0] == '1'; }();
-    if (disabled) return 0;
+    if (!fx_peer_sym_enabled()) return 0;
     constexpr int W = 12;                                  // doubles per rank in the exchange
     cudaStream_t s = ctx->stream;
     FX_TRY(peer_stage_alloc(ctx));

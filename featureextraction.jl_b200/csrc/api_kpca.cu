@@ -151,6 +151,20 @@ int fx_gramstage_run(fx_ctx* ctx, GramStage& g, const double* X, bool x_dev, int
             FX_TRY(fxcomm_allgather(ctx->comm, rs_loc, g.rowsum, (size_t)g.ld, s));
             tm.end();
         }
+        if (const char* dd = getenv("FXB200_DEBUG_DUMP")) {
+            // diagnostics: the all-gathered row sums and this rank's per-tile partials, one file per fit
+            static int fitno = 0;
+            std::vector<double> hrs((size_t)g.n_ld), hrp((size_t)fx_gram_rowpart_slots(g.n_ld) * g.ld);
+            FX_CUDA(cudaMemcpyAsync(hrs.data(), g.rowsum, hrs.size() * 8, cudaMemcpyDeviceToHost, s));
+            FX_CUDA(cudaMemcpyAsync(hrp.data(), g.rowpart, hrp.size() * 8, cudaMemcpyDeviceToHost, s));
+            FX_CUDA(cudaStreamSynchronize(s));
+            char path[512];
+            snprintf(path, sizeof(path), "%s/rowsum_r%d.bin", dd, ctx->rank);
+            if (FILE* f = fopen(path, "wb")) { fwrite(hrs.data(), 8, hrs.size(), f); fclose(f); }
+            snprintf(path, sizeof(path), "%s/rowpart_r%d.bin", dd, ctx->rank);
+            if (FILE* f = fopen(path, "wb")) { fwrite(hrp.data(), 8, hrp.size(), f); fclose(f); }
+            ++fitno;
+        }
         tm.begin(&st->center_ms);
         FX_TRY(fx_launch_means(ctx, g.rowsum, g.n, g.n_ld, g.colmean, g.scal));
         if (!g.defer_center) {

@@ -24,18 +24,28 @@ def _run(world, port, env_extra=None):
     return r.stdout
 
 
-# world 2: the two blocks are "opposite" (checkerboard split of the off-diagonal block);
-# world 3: odd ring, every off-diagonal block has one owner; world 4: both kinds at once
+# The default schedule is rank-local (each rank computes its whole row block; no peer stores).
 @pytest.mark.parametrize("world", [2, 3, 4])
-def test_sharded_fit_peer_symmetric_gram(world):
+def test_sharded_fit_rank_local_gram(world):
     out = _run(world, 29640 + world)
+    assert "peer=1" not in out
     print(out)
 
 
-def test_two_gpu_sharded_fit_without_peer_access():
-    """FXB200_NO_PEER=1: every rank computes its whole row block (the path taken when CUDA IPC /
-    NVLink peer access is unavailable); same results."""
-    out = _run(2, 29649, {"FXB200_NO_PEER": "1"})
+# Opt-in cross-rank symmetric Gram (FXB200_PEER_SYM=1; see DESIGN.md section 7 for why it is not the
+# default).  world 2: the two blocks are "opposite" (checkerboard split of the off-diagonal block);
+# world 3: odd ring, every off-diagonal block has one owner; world 4: both kinds at once
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_sharded_fit_peer_symmetric_gram(world):
+    out = _run(world, 29650 + world, {"FXB200_PEER_SYM": "1"})
+    assert "peer=1" in out
+    print(out)
+
+
+def test_peer_switch_off_wins():
+    """FXB200_NO_PEER=1 overrides the opt-in (the path taken when CUDA IPC / NVLink peer access is
+    unavailable); same results."""
+    out = _run(2, 29649, {"FXB200_NO_PEER": "1", "FXB200_PEER_SYM": "1"})
     assert "peer=1" not in out
 
 
