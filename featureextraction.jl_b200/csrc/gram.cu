@@ -53,6 +53,7 @@ struct GramParams {
     int kt;
     int tiles_x, tiles_y; long tiles_total;
     int sym;                          // 0 / 1 / 2, see the header comment
+    unsigned zero;                    // 0 at run time, opaque to the compiler (see the release of a stage)
     int rank, world;                  // sym == 2: this rank's block index and the number of blocks
     double* peerK[16];                // sym == 2: K of rank c (own entry = K)
     double* peerRowpart[16];          //           rowpart of rank c (or null)
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
             mbar_wait(&full[s], (it / STAGES) & 1);
             const double* As = smem + (size_t)s * STAGE_D + wm * 64 + g;
             const double* Bs = smem + (size_t)s * STAGE_D + BK * AS + wn * 32 + g;
+            unsigned dep = 0;
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) {
                 double a[8], b[4];
@@ -351,13 +353,31 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams p) {
                 for (int mt = 0; mt < 8; ++mt) a[mt] = As[kr * AS + mt * 8];
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[kr * BS + nt * 8];
+                if (kk == BK / 4 - 1 && p.sym == 2) {
+                    // see the release below: the barrier address is made to depend on the last fragments
+#pragma unroll
+                    for (int mt = 0; mt < 8; ++mt) dep |= (unsigned)__double2hiint(a[mt]);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) dep |= (unsigned)__double2hiint(b[nt]);
+                    dep &= p.zero;
+                }
 #pragma unroll
                 for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
             }
+            // Release of stage s.  ptxas schedules the arrive right behind the last LDS of the stage, ahead
+            // of the DMMAs that consume them.  With the load/store queue backed up by REMOTE stores (mirror
+            // epilogues of the cross-rank symmetric schedule, sym == 2) the arrive was observed to overtake
+            // those loads: the producer refilled the stage and one warp read the NEXT slab for its last
+            // 8-column fragment -- one 64 x 8 sub-block of K off, about 1 fit in 50 on four GPUs
+            // (profiles/r02_peer_sym_investigation.md).  In that mode the barrier address DEPENDS on the
+            // last fragments (p.zero is 0, but only at run time), so the arrive cannot issue before those
+            // loads have returned: 0 events in 500 fits.  Without remote stores the effect was never
+            // seen (every single-GPU bench line compares two fits bit for bit) and the dependency costs
+            // 2-6 % of the kernel, so the other modes release as before.
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);               // this warp is done with stage s
+            if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(&empty[s]) + dep));
         }
 
         // ---- epilogue: map in registers, shuffle row sums, direct 16-byte stores ----
@@ -451,7 +471,7 @@ int fx_launch_gram(fx_ctx* ctx, const GramArgs& a, int variant) {
     // whole symmetric matrix on one rank: only tiles on / right of the diagonal block are computed
     p.sym = (a.sym_source && a.diag_shift >= 0 && a.diag_shift % BM == 0 &&
              a.diag_shift + a.rows_pad <= a.ldk && !a.no_symmetry) ? 1 : 0;
-    p.rank = 0; p.world = 1;
+    p.rank = 0; p.world = 1; p.zero = 0;
     for (int c = 0; c < 16; ++c) { p.peerK[c] = nullptr; p.peerRowpart[c] = nullptr; }
     if (p.sym && a.peer_world > 1) {
         // cross-rank symmetry: needs every rank's block to be rows_pad wide and all peers mapped

@@ -22,7 +22,12 @@ def main():
     first = None
     bad = 0
     for f in range(fits):
-        V, L, st = fxb200.kpca(X, kern, k=k, ctx=h.ctx, return_stats=True)
+        try:
+            V, L, st = fxb200.kpca(X, kern, k=k, ctx=h.ctx, return_stats=True)
+        except fxb200.FxError as e:                 # e.g. not converged on a corrupted K: an event, keep going
+            bad += 1
+            print("rank %d fit %d FAILED: %s" % (h.rank, f, str(e)[:120]), flush=True)
+            continue
         key = (hashlib.sha1(L.tobytes()).hexdigest()[:12], repr(st["trace"]))
         if first is None:
             first = (key, L.copy())
