@@ -83,3 +83,37 @@ def test_block_orthonormalisation_cholqr_and_svqb_fallback():
     Qd, Cd, ndd = P.svqb(Wd, ops)
     assert ndd == 6
     np.testing.assert_allclose(Qd @ Cd, Wd, rtol=0, atol=1e-9 * np.abs(Wd).max())
+
+
+def test_merged_reprojection_and_block_gram_downdate():
+    """solver.cu::reproject_and_orthonormalise reduces Hs = [Q W]'W ONCE and takes the Gram matrix of the
+    re-projected block as G = W'W - H2'H2 (smalldense.cu gram_downdate_kernel) instead of forming
+    W - Q H2 first and reducing a second time.  That is safe because H2 is a SECOND-pass coefficient block
+    (~1e-8 of W after the first Gram-Schmidt pass), so the subtraction cannot cancel: the downdated Gram
+    equals the explicit one to rounding and CholQR from it gives an orthonormal block orthogonal to Q."""
+    import proto_krylov as P
+    rng = np.random.default_rng(17)
+    n, m, b = 4000, 48, 16
+    Q, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    W0 = rng.standard_normal((n, b)) * np.logspace(0, 2, b)[None, :] + Q @ rng.standard_normal((m, b)) * 50.0
+    W = W0 - Q @ (Q.T @ W0)                              # first pass (project_out)
+    H2 = Q.T @ W                                         # second-pass coefficients: tiny
+    assert np.abs(H2).max() <= 1e-11 * np.abs(W).max() * n ** 0.5
+    G_merged = W.T @ W - H2.T @ H2
+    Wp = W - Q @ H2
+    G_explicit = Wp.T @ Wp
+    assert np.abs(G_merged - G_explicit).max() <= 1e-14 * np.abs(G_explicit).max()
+    d = np.sqrt(np.diag(G_merged))
+    fac = P.chol_factors(G_merged / np.outer(d, d), 1e-8)
+    assert fac is not None
+    L = np.linalg.cholesky(G_merged)
+    Wo = np.linalg.solve(L, Wp.T).T                      # (W - Q H2) L^-T
+    assert np.abs(Wo.T @ Wo - np.eye(b)).max() <= 1e-12
+    assert np.abs(Q.T @ Wo).max() <= 1e-13
+    # the same identity would NOT be safe with FIRST-pass coefficients (a block with a large component
+    # inside span(Q)): there it cancels, which is why only the second pass is merged
+    Wb = rng.standard_normal((n, b)) + Q @ rng.standard_normal((m, b)) * 1e6
+    H1 = Q.T @ Wb
+    Wb_p = Wb - Q @ H1
+    G_bad = Wb.T @ Wb - H1.T @ H1
+    assert np.abs(G_bad - Wb_p.T @ Wb_p).max() > 1e-6 * np.abs(Wb_p.T @ Wb_p).max()
